@@ -1,0 +1,204 @@
+/* stablets_b200.h -- C ABI of the B200 (sm_100a) kernel library behind stable-ts's word-timestamp hot path.
+ *
+ * Drop-in boundary.  stable-ts is pure Python: the arithmetic of this path lives in the
+ * third-party `openai-whisper` package that stable_whisper/whisper_compatibility.py:58-76 imports.  Each entry point
+ * below replaces one of those calls (or the tensor post-processing stable-ts itself does around them) and is what a
+ * ctypes binding in the reference would load (see INTEGRATION.md for the stub).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - no allocation inside: the caller (PyTorch) owns inputs, outputs and workspaces;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), nothing synchronises;
+ *   - return value: STB_OK or an STB_ERR_* code; stb_last_error() gives the thread-local message;
+ *   - "split" matrices are fp16 hi/lo plane pairs with hi + lo == fp32 value to ~2^-22; in STB_PREC_FP16 mode the
+ *     lo plane pointer is NULL and only one tensor-core pass is issued.
+ */
+#ifndef STABLETS_B200_H
+#define STABLETS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(STB_BUILDING)
+#define STB_API __attribute__((visibility("default")))
+#else
+#define STB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STB_OK 0
+#define STB_ERR_ARG 1
+#define STB_ERR_CUDA 2
+#define STB_ERR_UNSUPPORTED 3
+
+#define STB_PREC_FP16 1   /* one fp16 tensor-core pass (what the reference's CUDA transcribe path computes in) */
+#define STB_PREC_FP16X3 3 /* hi*hi + hi*lo + lo*hi: fp32-grade products, the parity mode (reference CPU path is fp32) */
+
+#define STB_N_FRAMES 3000      /* mel frames per 30 s window (whisper_compatibility.py:87) */
+#define STB_N_AUDIO_CTX 1500   /* encoder positions per window */
+#define STB_KPAD 1504          /* 1500 rounded up to a multiple of 8: row pitch of score / probability matrices */
+
+STB_API const char* stb_last_error(void);
+STB_API int stb_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * a1  log-mel front-end.  Replaces whisper.audio.log_mel_spectrogram + pad_or_trim
+ *     (call sites stable_whisper/alignment.py:411-413, :660-661; original_whisper.py:528-530).
+ *     audio [B][n_samples] fp32; samples n_samples..padded_samples-1 are zeros (align: padded_samples = 480000;
+ *     refine: padded_samples = n_samples).  Frames = padded_samples/160, frames beyond are written as 0.0 (pad_or_trim).
+ *     batch_global_max != 0: the "max - 8" floor uses the max over the whole batch (alignment.py:660), else per item.
+ *     mel_out [B][n_mels][3000] fp32.  dft_table [400][2] fp32 (cos,sin of 2*pi*j/400), window [400] fp32,
+ *     filters [n_mels][201] fp32 are passed in by the host (computed once).  ws >= B*4 bytes.
+ * ---------------------------------------------------------------------------------------------------------- */
+STB_API int stb_logmel(const float* audio, int B, int n_samples, int padded_samples, int n_mels, const float* filters,
+               const float* window, const float* dft_table, int batch_global_max, float* mel_out, void* ws,
+               size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * GEMM core (K3): D[b,h] = epilogue(alpha * A[b,h] * B[b,h]^T), tcgen05.mma (kind::f16, fp32 accumulate in TMEM) fed
+ * by TMA.  Both operands are K-major split-fp16 4-D views (batch b, head h, row, k); strides in ELEMENTS.
+ * Exposed for tests; the model entry points below are sequences of these launches.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    const void* hi;        /* fp16 plane */
+    const void* lo;        /* fp16 plane or NULL (single pass) */
+    int rows;              /* rows per (b,h) slice (M for A, N for B) */
+    int k;                 /* reduction length (any; tiles beyond are zero-filled by TMA) */
+    long long row_stride;  /* elements; may be smaller than k (overlapping rows: conv-as-GEMM) */
+    long long h_stride;
+    long long b_stride;
+} stb_operand;
+
+#define STB_ACT_NONE 0
+#define STB_ACT_GELU 1
+
+typedef struct {
+    float* out_f32;        /* fp32 output or NULL */
+    void* out_hi;          /* split fp16 output planes or NULL */
+    void* out_lo;
+    long long ld_out;      /* elements; normal: off = m*ld_out + n; transposed: off = n*ld_out + m */
+    long long out_h_stride;
+    long long out_b_stride;
+    int transposed;
+    const float* bias;     /* [N] (or [M] when bias_per_row) or NULL */
+    int bias_per_row;
+    const float* residual; /* fp32, added after the activation; may alias out_f32 */
+    long long ld_res;
+    long long res_h_stride;
+    long long res_b_stride;
+    float alpha;
+    int act;
+} stb_epilogue;
+
+STB_API int stb_gemm(const stb_operand* A, const stb_operand* B, int n_batch, int n_head, const stb_epilogue* ep, void* stream);
+
+/* fp32 [rows][cols] (row pitch src_ld) -> split planes (row pitch dst_ld); lo may be NULL */
+STB_API int stb_split_f16(const float* src, long long rows, int cols, long long src_ld, void* hi, void* lo, long long dst_ld,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Model handle: dims + table of caller-owned device weight pointers (already packed, see stable-ts_b200/model.py).
+ * Replaces whisper.model.Whisper (encoder / decoder / cross-attention QK capture), reference call sites
+ * stable_whisper/timing.py:50-61, decode.py:27-40, alignment.py:660-667.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int n_mels, n_audio_ctx, n_audio_state, n_audio_head, n_audio_layer;
+    int n_vocab, n_text_ctx, n_text_state, n_text_head, n_text_layer;
+} stb_dims;
+
+typedef struct stb_model stb_model;
+
+/* tensor ids for stb_model_set_tensor; `layer` is ignored for the non-layer tensors */
+enum {
+    STB_T_ENC_CONV1_W = 0, /* split [d][3*n_mels], k index = tap*n_mels + c_in */
+    STB_T_ENC_CONV1_B,     /* f32 [d] */
+    STB_T_ENC_CONV2_W,     /* split [d][3*d], k index = tap*d + c_in */
+    STB_T_ENC_CONV2_B,
+    STB_T_ENC_POS,         /* f32 [1500][d] */
+    STB_T_ENC_LNPOST_G,
+    STB_T_ENC_LNPOST_B,
+    STB_T_DEC_TOKEMB_F32,  /* f32 [V][d] (embedding gather) */
+    STB_T_DEC_TOKEMB,      /* split [V][d] (logits GEMM) */
+    STB_T_DEC_POS,         /* f32 [n_text_ctx][d] */
+    STB_T_DEC_LN_G,
+    STB_T_DEC_LN_B,
+    STB_T_LAYER_BASE = 32,
+    /* per-layer ids (add to STB_T_LAYER_BASE); encoder layers use ENC_*, decoder layers DEC_* */
+    STB_L_ATTN_LN_G = 0, STB_L_ATTN_LN_B, STB_L_QKV_W /* split [3d][d]: q,k,v */, STB_L_QKV_B /* f32 [3d], k part 0 */,
+    STB_L_OUT_W, STB_L_OUT_B, STB_L_MLP_LN_G, STB_L_MLP_LN_B, STB_L_FC1_W, STB_L_FC1_B, STB_L_FC2_W, STB_L_FC2_B,
+    STB_L_CROSS_LN_G, STB_L_CROSS_LN_B, STB_L_CQ_W, STB_L_CQ_B, STB_L_CKV_W /* split [2d][d]: k,v */,
+    STB_L_CKV_B /* f32 [2d], k part 0 */, STB_L_COUT_W, STB_L_COUT_B,
+    STB_L_COUNT
+};
+
+STB_API int stb_model_create(const stb_dims* dims, int precision, stb_model** out);
+STB_API void stb_model_destroy(stb_model* m);
+/* is_decoder: 0 encoder layer table, 1 decoder layer table (only for ids >= STB_T_LAYER_BASE) */
+STB_API int stb_model_set_tensor(stb_model* m, int tensor_id, int is_decoder, int layer, const void* p_hi_or_f32, const void* p_lo);
+
+/* a2 encoder: mel [B][n_mels][3000] fp32 -> xa_f32 [B][1500][d] (+ split planes for the cross K/V GEMMs). */
+STB_API size_t stb_encoder_ws_bytes(const stb_model* m, int B);
+STB_API int stb_encoder_forward(stb_model* m, const float* mel, int B, float* xa_f32, void* xa_hi, void* xa_lo, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* cross-attention K and V^T of every decoder layer, computed once per window (whisper's kv_cache for cross_attn). */
+STB_API size_t stb_cross_kv_bytes(const stb_model* m, int B);
+STB_API int stb_cross_kv(stb_model* m, const void* xa_hi, const void* xa_lo, int B, void* cross_kv, void* ws, size_t ws_bytes,
+                 void* stream);
+
+/* a3 teacher-forced decoder with cross-attention capture (stable_whisper/timing.py:50-61 under disable_sdpa).
+ *   tokens [B][M] int32.  logits (nullable) [B*M][ld_logits] fp32.
+ *   qk_out (nullable) fp32 [B][n_sel][M][STB_KPAD]: scaled PRE-softmax cross-attention scores of the selected
+ *   (layer, head) pairs sel_pairs_host[2*n_sel] (host array); n_sel < 0 selects all L*H heads in (layer, head) order. */
+STB_API size_t stb_decoder_ws_bytes(const stb_model* m, int B, int M);
+STB_API int stb_decoder_forward(stb_model* m, const int32_t* tokens, int B, int M, const void* cross_kv, float* logits,
+                        long long ld_logits, float* qk_out, const int32_t* sel_pairs_host, int n_sel, void* ws,
+                        size_t ws_bytes, void* stream);
+
+/* a4 / a10 token probabilities (stable_whisper/timing.py:62-64, alignment.py:669-671, refinement.py:305-325):
+ *   per row r: p = softmax(logits[row0 + r][:n_classes])[target[r]]; rank_out (nullable) = number of classes with
+ *   probability strictly smaller than the target's (== index of the target in the ascending sort, ties aside). */
+STB_API int stb_token_probs(const float* logits, long long ld, int n_rows, int n_classes, const int32_t* targets, float* prob_out,
+                    int32_t* rank_out, void* stream);
+
+/* a5 QK post-processing, legacy alignment-head path (stable_whisper/timing.py:105-110,194):
+ *   qk [B][A][M][ldq] fp32 (as written by stb_decoder_forward); rows S..M-2 (R = M-1-S rows), columns [0,F) ->
+ *   softmax(qk*qk_scale) over columns -> z-norm over the R rows of each column (biased std) -> median filter
+ *   (width, reflect) along columns -> mean over the A heads -> matrix [B][R][ldm] fp32.
+ *   ws >= stb_qkpost_ws_bytes. */
+STB_API size_t stb_qkpost_ws_bytes(int B, int A, int R, int F);
+STB_API int stb_qk_postprocess(const float* qk, int B, int A, int M, long long ldq, int S, int F, float qk_scale, int medfilt_width,
+                       float* matrix, long long ldm, void* ws, size_t ws_bytes, void* stream);
+
+/* a6 DTW + jump extraction (whisper.timing.dtw CPU semantics + stable_whisper/timing.py:195-198):
+ *   x [B][R][ldx] fp32 (cost = -x when negate != 0), path over the R x F grid, strict-'<' tie rule, fp32 cost.
+ *   jumps [B][R] int32 = first frame of every row on the path (clipped at 0).
+ *   path (nullable) [B][2][R+F] int32 = (text_idx, time_idx) in forward order, path_len [B]. */
+STB_API size_t stb_dtw_smem_bytes(int R, int F);
+STB_API int stb_dtw(const float* x, int B, int R, int F, long long ldx, int negate, int32_t* jumps, int32_t* path,
+            int32_t* path_len, void* stream);
+
+/* a9 KV-cached decode step(s): see stb_decode_* in the section below (decode.py:33-65). */
+STB_API size_t stb_decode_state_bytes(const stb_model* m, int B);
+STB_API size_t stb_decode_ws_bytes(const stb_model* m, int B);
+/* One decoder step for B sequences at position `pos` (0-based index of the token being fed):
+ *   tokens_in [B] int32 -> logits_out [B][ld_logits] fp32.  self-attention K/V are appended to `state`. */
+STB_API int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int pos, const void* cross_kv, void* state,
+                    float* logits_out, long long ld_logits, void* ws, size_t ws_bytes, void* stream);
+/* Logit filters + greedy pick for one step (decode.py:46-58 + whisper.decoding filters), in place on logits:
+ *   suppress_mask [V] uint8 (1 = -inf; SuppressTokens/SuppressBlank resolved by the host for this step),
+ *   ts_mask (nullable) [1501] uint8 silent-timestamp mask, timestamp rules from the per-sequence state
+ *   last_ts[B] (last timestamp token seen or -1), last_was_ts[B], penult_was_ts[B] (uint8),
+ *   is_first_step, max_initial_ts (or -1).  next_out [B] int32 = argmax (first max index), logprob_out [B] fp32. */
+STB_API int stb_sample_greedy(float* logits, long long ld, int B, int V, int eot, int ts_begin, int no_timestamps,
+                      const uint8_t* suppress_mask, const uint8_t* ts_mask, const int32_t* last_ts,
+                      const uint8_t* last_was_ts, const uint8_t* penult_was_ts, int is_first_step, int max_initial_ts,
+                      int apply_ts_rules, int32_t* next_out, float* logprob_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STABLETS_B200_H */

@@ -1,0 +1,215 @@
+// a6 / K7: monotone DTW + backtrack + jump extraction, one CTA per 30 s window.
+//
+// Replaces whisper.timing.dtw (CPU semantics: numba dtw_cpu + backtrace) and the jump extraction of
+// stable_whisper/timing.py:195-198.  Bit-exact contract: fp32 cost, strict '<' tie rule
+// (diag iff c0<c1 && c0<c2; up iff c1<c0 && c1<c2; else left), +inf borders, cost[0][0] = 0.
+//
+// Parallelisation (R <= 480 rows x F <= 1500 frames):
+//   * lane l of warp w owns row r = 32 w + l and walks its row left to right; within a warp the anti-diagonal
+//     wavefront is kept with ONE shuffle per step (up = lane-1's previous value, diag = the up of the previous step);
+//   * warps are software-pipelined: warp w+1 consumes the last row of warp w through a small shared-memory ring
+//     (256 columns) guarded by two monotone progress counters -- no block-wide barrier in the sweep;
+//   * x is staged in registers one 32-step block ahead (skewed per lane so the register index is static);
+//   * the trace is 2 bits per cell, packed 16 cells per word in shared memory (<= 169 KB), and the backtrack runs in
+//     the same kernel on one thread with the current trace word cached in a register.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace stb {
+
+constexpr int DTW_RING = 256;                 // columns per inter-warp boundary ring
+constexpr int DTW_RING_CHUNKS = DTW_RING / 32;
+constexpr int DTW_MAX_ROWS = 480;             // 15 warps
+
+__device__ __forceinline__ int vload(const volatile int* p) { return *p; }
+// bounded spin on a monotone shared-memory progress counter (a protocol bug traps instead of hanging the box)
+__device__ __forceinline__ void wait_ge(const volatile int* p, int need) {
+    if (vload(p) >= need) return;
+    const long long t0 = clock64();
+    while (vload(p) < need) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("stb: dtw progress timeout block=%d thread=%d need=%d have=%d\n", blockIdx.x, threadIdx.x, need, vload(p));
+            __trap();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DTW_MAX_ROWS, 1)
+dtw_kernel(const float* __restrict__ x, int R, int F, long long ldx, long long x_bstride, int negate,
+           int32_t* __restrict__ jumps, int32_t* __restrict__ path, int32_t* __restrict__ path_len) {
+    extern __shared__ uint32_t dsm[];
+    const int TW = (F + 15) >> 4;                              // trace words per row
+    const int NW = (R + 31) >> 5;
+    uint32_t* trace = dsm;                                     // [R][TW]
+    volatile float* ring = reinterpret_cast<volatile float*>(trace + (size_t)R * TW);   // [NW-1][DTW_RING]
+    volatile int* prod = reinterpret_cast<volatile int*>(const_cast<float*>(ring) + (size_t)(NW > 1 ? NW - 1 : 0) * DTW_RING);  // [NW]
+    volatile int* cons = prod + NW;                            // [NW]
+
+    const int b = blockIdx.x;
+    const int w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int r = w * 32 + lane;
+    const bool row_ok = r < R;
+    const float* xr_ptr = x + (long long)b * x_bstride + (long long)r * ldx;
+    const float INF = INFINITY;
+
+    if (threadIdx.x < NW) {
+        prod[threadIdx.x] = 0;
+        cons[threadIdx.x] = 0;
+    }
+    __syncthreads();
+
+    if (w < NW) {
+        const bool is_prod = w < NW - 1;
+        const bool is_cons = w > 0;
+        const volatile float* ring_in = ring + (size_t)(w - 1) * DTW_RING;     // valid if is_cons
+        volatile float* ring_out = ring + (size_t)w * DTW_RING;                // valid if is_prod
+        float own = INF;        // cost[r][j-1] (left)
+        float diag = INF;       // cost[r-1][j-1]
+        uint32_t tacc = 0;
+        const int n_blocks = (F + 31 + 31) >> 5;                      // ceil((F+31)/32)
+        float xc[32], xn[32];
+#pragma unroll
+        for (int s = 0; s < 32; ++s) {
+            const int col = s - lane;
+            xc[s] = (row_ok && col >= 0 && col < F) ? xr_ptr[col] : 0.f;
+        }
+#pragma unroll 1
+        for (int kb = 0; kb < n_blocks; ++kb) {
+            // prefetch the next block (skewed by lane): lands while this block's 32 dependent steps run
+#pragma unroll
+            for (int s = 0; s < 32; ++s) {
+                const int col = (kb + 1) * 32 + s - lane;
+                xn[s] = (row_ok && col >= 0 && col < F) ? xr_ptr[col] : 0.f;
+            }
+#pragma unroll
+            for (int s = 0; s < 32; ++s) {
+                const int t = kb * 32 + s;                            // warp-uniform step
+                const int j = t - lane;                               // this lane's column
+                // ---- flow control (warp-uniform conditions) ----
+                if (is_cons && (t & 31) == 0 && t < F) {              // lane 0 is about to read ring chunk t/32
+                    const int need = (t >> 5) + 1;
+                    wait_ge(&prod[w - 1], need);
+                }
+                if (is_prod) {
+                    const int jp = t - 31;                            // lane 31's column
+                    if (jp >= 0 && (jp & 31) == 0 && jp < F) {        // about to overwrite ring chunk (jp/32) % CHUNKS
+                        const int need = (jp >> 5) - (DTW_RING_CHUNKS - 1);
+                        wait_ge(&cons[w + 1], need);
+                    }
+                }
+                float up = __shfl_up_sync(0xffffffffu, own, 1);
+                if (lane == 0) up = (is_cons && t < F) ? ring_in[t & (DTW_RING - 1)] : INF;
+                if (row_ok && j >= 0 && j < F) {
+                    const float c0 = (j == 0) ? (r == 0 ? 0.f : INF) : diag;
+                    const float c1 = up;
+                    const float c2 = (j == 0) ? INF : own;
+                    float c;
+                    uint32_t code;
+                    if (c0 < c1 && c0 < c2) { c = c0; code = 0u; }
+                    else if (c1 < c0 && c1 < c2) { c = c1; code = 1u; }
+                    else { c = c2; code = 2u; }
+                    const float xv = negate ? -xc[s] : xc[s];
+                    own = xv + c;
+                    tacc |= code << ((j & 15) * 2);
+                    if ((j & 15) == 15 || j == F - 1) {
+                        trace[(size_t)r * TW + (j >> 4)] = tacc;
+                        tacc = 0;
+                    }
+                    if (is_prod && lane == 31) ring_out[j & (DTW_RING - 1)] = own;
+                }
+                diag = up;
+                // ---- publish progress ----
+                if (is_prod) {
+                    const int jp = t - 31;
+                    if (jp >= 0 && jp < F && ((jp & 31) == 31 || jp == F - 1)) {
+                        __threadfence_block();
+                        if (lane == 31) prod[w] = (jp >> 5) + 1;
+                    }
+                }
+                if (is_cons && t < F && ((t & 31) == 31 || t == F - 1)) {
+                    __threadfence_block();
+                    if (lane == 0) cons[w] = (t >> 5) + 1;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 32; ++s) xc[s] = xn[s];
+        }
+    }
+    __syncthreads();
+
+    // ---- backtrack (whisper.timing.backtrace): padded coords (i, j), emit (i-1, j-1) until (0, 0) ----
+    int32_t* pt = path ? path + (long long)b * 2 * (R + F) : nullptr;
+    int32_t* pj = pt ? pt + (R + F) : nullptr;
+    __shared__ int s_len;
+    if (threadIdx.x == 0) {
+        int i = R, j = F, n = 0;
+        int cached_row = -1, cached_word = -1;
+        uint32_t word = 0;
+        int32_t* jb = jumps + (long long)b * R;
+        while (i > 0 || j > 0) {
+            if (pt) { pt[n] = i - 1; pj[n] = j - 1; }
+            if (i >= 1) jb[i - 1] = (j - 1) < 0 ? 0 : (j - 1);
+            ++n;
+            uint32_t code;
+            if (i == 0) code = 2u;                             // trace[0, :] = 2
+            else if (j == 0) code = 1u;                        // trace[:, 0] = 1
+            else {
+                const int rr = i - 1, cc = j - 1;
+                if (rr != cached_row || (cc >> 4) != cached_word) {
+                    cached_row = rr;
+                    cached_word = cc >> 4;
+                    word = trace[(size_t)rr * TW + cached_word];
+                }
+                code = (word >> ((cc & 15) * 2)) & 3u;
+            }
+            if (code == 0u) { --i; --j; }
+            else if (code == 1u) { --i; }
+            else { --j; }
+        }
+        s_len = n;
+        if (path_len) path_len[b] = n;
+    }
+    __syncthreads();
+    if (pt) {                                                  // reverse into forward order
+        const int n = s_len;
+        for (int k = threadIdx.x; k < n / 2; k += blockDim.x) {
+            int32_t a = pt[k]; pt[k] = pt[n - 1 - k]; pt[n - 1 - k] = a;
+            a = pj[k]; pj[k] = pj[n - 1 - k]; pj[n - 1 - k] = a;
+        }
+    }
+}
+
+static size_t dtw_smem(int R, int F) {
+    const int TW = (F + 15) >> 4, NW = (R + 31) >> 5;
+    return (size_t)R * TW * 4 + (size_t)(NW > 1 ? NW - 1 : 0) * DTW_RING * 4 + (size_t)NW * 2 * 4 + 16;
+}
+
+}  // namespace stb
+
+extern "C" size_t stb_dtw_smem_bytes(int R, int F) { return stb::dtw_smem(R, F); }
+
+extern "C" int stb_dtw(const float* x, int B, int R, int F, long long ldx, int negate, int32_t* jumps, int32_t* path,
+                       int32_t* path_len, void* stream) {
+    STB_REQUIRE(x && jumps, "stb_dtw: null pointer");
+    STB_REQUIRE(B >= 1 && R >= 1 && F >= 1 && R <= stb::DTW_MAX_ROWS && F <= 1504 && ldx >= F,
+                "stb_dtw: unsupported shape B=%d R=%d F=%d ld=%lld (R<=%d, F<=1504)", B, R, F, ldx, stb::DTW_MAX_ROWS);
+    const size_t smem = stb::dtw_smem(R, F);
+    static size_t max_dyn = 0;          // opt-in limit minus the kernel's static shared memory
+    if (max_dyn == 0) {
+        int dev = 0, optin = 0;
+        cudaFuncAttributes fa;
+        STB_CUDA_OK(cudaGetDevice(&dev));
+        STB_CUDA_OK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        STB_CUDA_OK(cudaFuncGetAttributes(&fa, stb::dtw_kernel));
+        const size_t lim = (size_t)optin - fa.sharedSizeBytes;
+        STB_CUDA_OK(cudaFuncSetAttribute(stb::dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        max_dyn = lim;
+    }
+    STB_REQUIRE(smem <= max_dyn, "stb_dtw: trace needs %zu B of shared memory (limit %zu)", smem, max_dyn);
+    const int NW = (R + 31) / 32;
+    stb::dtw_kernel<<<B, NW * 32, smem, (cudaStream_t)stream>>>(x, R, F, ldx, (long long)R * ldx, negate, jumps, path, path_len);
+    STB_LAUNCH_OK();
+    return STB_OK;
+}

@@ -1,0 +1,27 @@
+// Internal (non-ABI) declarations shared between the translation units of libstablets_b200.so.
+#pragma once
+#include "common.cuh"
+
+namespace stb {
+
+struct CaptureList {          // passed by value to the capture kernel
+    int count;
+    int head[32];             // head index inside the layer
+    int slot[32];             // destination index inside qk_out's n_sel dimension
+};
+
+int gemm(const stb_operand& A, const stb_operand& B, int n_batch, int n_head, const stb_epilogue& ep, cudaStream_t st);
+
+int layernorm(const float* x, long long rows, int d, const float* gamma, const float* beta, __half* hi, __half* lo,
+              float* out_f32, cudaStream_t st);
+int softmax_rows(const float* S, long long n_rows, int n_cols, long long ld_s, int rows_per_slice, int causal, __half* hi,
+                 __half* lo, long long ld_p, cudaStream_t st);
+int embed_tokens(const int32_t* tokens, long long n_tok, int M, int offset, int d, const float* emb, const float* pos,
+                 float* x, cudaStream_t st);
+int mel_repack(const float* mel, int B, int C, int T, __half* hi, __half* lo, cudaStream_t st);
+int zero_pad_rows(__half* hi, __half* lo, int B, int C, int T, cudaStream_t st);
+int im2col3(const __half* src, int B, int C, int Tin_pad, int Tout, int stride, __half* dst, cudaStream_t st);
+int capture_heads(const float* S, int B, int H, int M, long long ld, float* out, int n_sel, const CaptureList& list,
+                  cudaStream_t st);
+
+}  // namespace stb

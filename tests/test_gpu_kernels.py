@@ -1,0 +1,298 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the CPU oracle on seeded inputs.
+
+Run on the B200 box:  python -m pytest tests -m gpu -q
+The oracle (oracle/) is the checker only; the thing under test is libstablets_b200.so called through ctypes.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def L():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from stable_ts_b200 import _lib
+    _lib.lib()
+    return _lib
+
+
+def _split(x, lo=True):
+    hi = x.half()
+    return hi, ((x - hi.float()).half() if lo else None)
+
+
+def _gemm(L, A, B, passes=3, bias=None, act=0, residual=None, alpha=1.0, out="f32", transposed=False):
+    """A [M,K], B [N,K] fp32 cuda -> D via stb_gemm."""
+    M, K = A.shape
+    N = B.shape[0]
+    ah, al = _split(A, passes == 3)
+    bh, bl = _split(B, passes == 3)
+    opa = L.Operand(L.ptr(ah), L.ptr(al), M, K, K, 0, 0)
+    opb = L.Operand(L.ptr(bh), L.ptr(bl), N, K, K, 0, 0)
+    shape = (N, M) if transposed else (M, N)
+    ld = shape[1]
+    ldp = (ld + 7) // 8 * 8
+    of = torch.full((shape[0], ldp), float("nan"), device="cuda") if out == "f32" else None
+    oh = torch.zeros(shape[0], ldp, dtype=torch.float16, device="cuda") if out == "split" else None
+    ol = torch.zeros(shape[0], ldp, dtype=torch.float16, device="cuda") if out == "split" else None
+    ep = L.Epilogue()
+    ep.out_f32, ep.out_hi, ep.out_lo = L.ptr(of), L.ptr(oh), L.ptr(ol)
+    ep.ld_out = ldp
+    ep.transposed = int(transposed)
+    ep.bias = L.ptr(bias)
+    ep.residual = L.ptr(residual)
+    ep.ld_res = residual.stride(0) if residual is not None else 0
+    ep.alpha = alpha
+    ep.act = act
+    L.check(L.lib().stb_gemm(ctypes.byref(opa), ctypes.byref(opb), 1, 1, ctypes.byref(ep), L.stream_ptr()))
+    torch.cuda.synchronize()
+    if out == "f32":
+        return of[:, :ld]
+    return oh[:, :ld].float() + ol[:, :ld].float()
+
+
+def _ref(A, B, bias=None, act=0, residual=None, alpha=1.0):
+    D = alpha * (A.double().cpu() @ B.double().cpu().T)
+    if bias is not None:
+        D = D + bias.double().cpu()
+    if act == 1:
+        D = torch.nn.functional.gelu(D)
+    if residual is not None:
+        D = D + residual.double().cpu()
+    return D
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 128, 256), (300, 200, 192), (1500, 384, 384), (77, 1000, 128),
+                                   (256, 64, 1504), (130, 16, 64), (200, 40, 320), (64, 51866, 128)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_gemm_plain(L, M, N, K, passes):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g) * 0.3
+    D = _gemm(L, A, B, passes).double().cpu()
+    R = _ref(A, B)
+    err = (D - R).abs().max().item() / R.abs().max().item()
+    print(f"gemm {M}x{N}x{K} passes={passes}: rel err {err:.3e}")
+    assert torch.isfinite(D).all()
+    assert err < (max(3e-6, 2e-7 * K ** 0.5 * 2) if passes == 3 else 3e-3)   # grows ~sqrt(K)
+
+
+def test_gemm_epilogues(L):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    M, N, K = 333, 264, 448
+    A = torch.randn(M, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g) * 0.2
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(M, N, device="cuda", generator=g)
+    for kw in [dict(bias=bias), dict(bias=bias, act=1), dict(bias=bias, residual=res), dict(alpha=0.125),
+               dict(bias=bias, act=1, residual=res)]:
+        D = _gemm(L, A, B, 3, **kw).double().cpu()
+        R = _ref(A, B, **kw)
+        err = (D - R).abs().max().item() / R.abs().max().item()
+        print("epilogue", {k: (v if not torch.is_tensor(v) else "T") for k, v in kw.items()}, f"{err:.3e}")
+        assert err < 5e-6
+    D = _gemm(L, A, B, 3, bias=bias, act=1, out="split").double().cpu()
+    R = _ref(A, B, bias=bias, act=1)
+    assert (D - R).abs().max().item() / R.abs().max().item() < 5e-6
+    D = _gemm(L, A, B, 3, bias=bias, out="split", transposed=True).double().cpu()
+    assert (D - _ref(A, B, bias=bias).T).abs().max().item() < 5e-5
+    D = _gemm(L, A, B, 3, out="f32", transposed=True).double().cpu()
+    assert (D - _ref(A, B).T).abs().max().item() < 5e-5
+
+
+def test_gemm_batched_head_views(L):
+    """q k^T over a fused [B*T][2d] buffer: 4-D operand views with head and batch strides (attention scores)."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    Bn, H, T, d = 2, 3, 150, 192
+    qk = torch.randn(Bn * T, 2 * d, device="cuda", generator=g)
+    hi, lo = _split(qk)
+    opa = L.Operand(L.ptr(hi), L.ptr(lo), T, 64, 2 * d, 64, T * 2 * d)
+    opb = L.Operand(hi.data_ptr() + d * 2, lo.data_ptr() + d * 2, T, 64, 2 * d, 64, T * 2 * d)
+    ldk = (T + 7) // 8 * 8
+    S = torch.full((Bn, H, T, ldk), float("nan"), device="cuda")
+    ep = L.Epilogue()
+    ep.out_f32 = L.ptr(S)
+    ep.ld_out, ep.out_h_stride, ep.out_b_stride = ldk, T * ldk, H * T * ldk
+    ep.alpha = 0.125
+    L.check(L.lib().stb_gemm(ctypes.byref(opa), ctypes.byref(opb), Bn, H, ctypes.byref(ep), L.stream_ptr()))
+    torch.cuda.synchronize()
+    x = qk.double().cpu().view(Bn, T, 2, H, 64)
+    R = 0.125 * torch.einsum("bthc,bshc->bhts", x[:, :, 0], x[:, :, 1])
+    err = (S[..., :T].double().cpu() - R).abs().max().item() / R.abs().max().item()
+    print(f"batched head-view gemm rel err {err:.3e}")
+    assert err < 3e-6
+
+
+@pytest.mark.parametrize("stride_mult,C", [(1, 80), (2, 128)])
+def test_gemm_overlapping_rows_is_conv(L, stride_mult, C):
+    """conv1d(k=3, pad=1, stride s) as a GEMM over an overlapping-row TMA view of the time-major padded input."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    Tin, Cout = 600, 96
+    x = torch.randn(1, C, Tin, device="cuda", generator=g)
+    w = torch.randn(Cout, C, 3, device="cuda", generator=g) * 0.1
+    Tout = (Tin + 2 - 3) // stride_mult + 1
+    xt = torch.zeros(Tin + 2, C, device="cuda")
+    xt[1:Tin + 1] = x[0].T
+    hi, lo = _split(xt)
+    wh, wl = _split(w.permute(0, 2, 1).reshape(Cout, 3 * C).contiguous())
+    opa = L.Operand(L.ptr(hi), L.ptr(lo), Tout, 3 * C, stride_mult * C, 0, 0)
+    opb = L.Operand(L.ptr(wh), L.ptr(wl), Cout, 3 * C, 3 * C, 0, 0)
+    out = torch.full((Tout, Cout), float("nan"), device="cuda")
+    ep = L.Epilogue()
+    ep.out_f32, ep.ld_out, ep.alpha = L.ptr(out), Cout, 1.0
+    L.check(L.lib().stb_gemm(ctypes.byref(opa), ctypes.byref(opb), 1, 1, ctypes.byref(ep), L.stream_ptr()))
+    torch.cuda.synchronize()
+    R = torch.nn.functional.conv1d(x.double().cpu(), w.double().cpu(), padding=1, stride=stride_mult)[0].T
+    err = (out.double().cpu() - R).abs().max().item() / R.abs().max().item()
+    print(f"conv-as-gemm stride {stride_mult} C {C}: rel err {err:.3e}")
+    assert err < 3e-6
+
+
+# --------------------------------------------------------------------------------------------------------- DTW
+def _dtw_gpu(L, x, negate=False, want_path=True):
+    from stable_ts_b200 import _lib
+    B, R, F = x.shape
+    jumps = torch.empty(B, R, dtype=torch.int32, device="cuda")
+    path = torch.empty(B, 2, R + F, dtype=torch.int32, device="cuda")
+    plen = torch.empty(B, dtype=torch.int32, device="cuda")
+    L.check(L.lib().stb_dtw(L.ptr(x), B, R, F, x.stride(1), int(negate), L.ptr(jumps), L.ptr(path), L.ptr(plen),
+                            L.stream_ptr()))
+    torch.cuda.synchronize()
+    return jumps.cpu().numpy(), path.cpu().numpy(), plen.cpu().numpy()
+
+
+@pytest.mark.parametrize("R,F,quant", [(1, 7, False), (9, 1, False), (7, 31, False), (33, 64, False), (41, 333, True),
+                                       (101, 937, False), (106, 1500, False), (230, 1500, False), (449, 1500, False),
+                                       (449, 1500, True), (64, 33, False)])
+def test_dtw_bit_exact_vs_oracle(L, R, F, quant):
+    from oracle import c_oracle
+    rng = np.random.default_rng(R * 10007 + F)
+    Bn = 3
+    x = rng.standard_normal((Bn, R, F)).astype(np.float32)
+    if quant:
+        x = np.round(x * 2) / 2            # many exact ties: exercises the strict-'<' rule
+    jumps, path, plen = _dtw_gpu(L, torch.from_numpy(x).cuda())
+    for b in range(Bn):
+        p_ref, j_ref = c_oracle.dtw(x[b])
+        n = int(plen[b])
+        assert n == p_ref.shape[1], (n, p_ref.shape)
+        assert np.array_equal(path[b, :, :n], p_ref)
+        assert np.array_equal(jumps[b], j_ref)
+
+
+def test_dtw_goldens_from_reference(L):
+    z = np.load(os.path.join(GOLD, "dtw_cases.npz"))
+    for i in range(3):
+        x, p = z[f"x{i}"], z[f"p{i}"]
+        jumps, path, plen = _dtw_gpu(L, torch.from_numpy(x)[None].cuda(), negate=True)
+        assert np.array_equal(path[0, :, :int(plen[0])], p)
+
+
+def test_dtw_nan_and_strided_rows(L):
+    from oracle import c_oracle
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 20, 104)).astype(np.float32)
+    x[0, 5] = np.nan
+    xt = torch.from_numpy(x).cuda()
+    jumps, path, plen = _dtw_gpu(L, xt[:, :, :101])            # row pitch 104, F = 101
+    for b in range(2):
+        p_ref, j_ref = c_oracle.dtw(x[b, :, :101])
+        assert np.array_equal(path[b, :, :int(plen[b])], p_ref)
+        assert np.array_equal(jumps[b], j_ref)
+
+
+# --------------------------------------------------------------------------------------------------------- QK post
+@pytest.mark.parametrize("A,M,F,S", [(6, 44, 937, 1), (10, 109, 1500, 3), (3, 12, 50, 3), (2, 6, 3, 1)])
+def test_qk_postprocess_vs_oracle(L, A, M, F, S):
+    from oracle import stable_path as SP
+    g = torch.Generator().manual_seed(A * 100 + M)
+    Bn = 2
+    qk = torch.randn(Bn, A, M, 1504, generator=g) * 2.0
+    lib = L.lib()
+    R = M - 1 - S
+    ldm = (F + 3) // 4 * 4
+    out = torch.empty(Bn, R, ldm, device="cuda")
+    ws = torch.empty(lib.stb_qkpost_ws_bytes(Bn, A, R, F), dtype=torch.uint8, device="cuda")
+    qkc = qk.cuda()
+    L.check(lib.stb_qk_postprocess(L.ptr(qkc), Bn, A, M, 1504, S, F, 1.0, 7, L.ptr(out), ldm, L.ptr(ws), ws.numel(),
+                                   L.stream_ptr()))
+    torch.cuda.synchronize()
+    for b in range(Bn):
+        qks = [qk[b:b + 1, a:a + 1] for a in range(A)]           # one "layer" per head, head index 0
+        w = SP.attention_weights_legacy(qks, [(a, 0) for a in range(A)], S, F * 320)
+        ref = w.mean(dim=0)
+        got = out[b, :, :F].cpu()
+        err = (got - ref).abs().max().item()
+        print(f"qkpost A={A} M={M} F={F}: max abs err {err:.3e}")
+        assert err < 2e-5
+
+
+# --------------------------------------------------------------------------------------------------------- log-mel
+@pytest.mark.parametrize("n,n_mels", [(480000, 80), (300000, 128), (123457, 80)])
+def test_logmel_align_mode_vs_oracle(L, n, n_mels):
+    from oracle import stable_path as SP
+    from oracle.whisper_ref import audio as A
+    from stable_ts_b200.model import mel_filterbank
+    assert np.array_equal(mel_filterbank(n_mels), A.mel_filterbank_np(n_mels))
+    x = SP.synth_audio(n, seed=n % 1000)
+    ref = A.pad_or_trim(A.log_mel_spectrogram(x, n_mels, padding=480000 - n), 3000)
+    got = _logmel(L, x[None].cuda(), 480000, n_mels, False)[0].cpu()
+    err = (got - ref).abs().max().item()
+    print(f"logmel n={n} mels={n_mels}: max abs err {err:.3e}")
+    assert err < 2e-4
+
+
+def test_logmel_refine_mode_batch_global_max(L):
+    from oracle import stable_path as SP
+    from oracle.whisper_ref import audio as A
+    n = 200000
+    x = torch.stack([SP.synth_audio(n, seed=1), 0.05 * SP.synth_audio(n, seed=2)])
+    ref = A.pad_or_trim(A.log_mel_spectrogram(x, 80), 3000)
+    got = _logmel(L, x.cuda(), n, 80, True).cpu()
+    err = (got - ref).abs().max().item()
+    print(f"logmel refine-mode: max abs err {err:.3e}")
+    assert err < 2e-4
+    assert (got[:, :, n // 160:] == 0).all()
+
+
+def _logmel(L, audio, padded, n_mels, global_max):
+    from stable_ts_b200.model import mel_filterbank
+    B, n = audio.shape
+    k = np.arange(400, dtype=np.float64)
+    window = torch.from_numpy((0.5 - 0.5 * np.cos(2 * np.pi * k / 400)).astype(np.float32)).cuda()
+    dft = torch.from_numpy(np.stack([np.cos(2 * np.pi * k / 400), np.sin(2 * np.pi * k / 400)], 1).astype(np.float32)).cuda()
+    filt = torch.from_numpy(mel_filterbank(n_mels)).cuda()
+    mel = torch.empty(B, n_mels, 3000, device="cuda")
+    ws = torch.empty(B * 376 * 4, dtype=torch.uint8, device="cuda")
+    L.check(L.lib().stb_logmel(L.ptr(audio), B, n, padded, n_mels, L.ptr(filt), L.ptr(window), L.ptr(dft), int(global_max),
+                               L.ptr(mel), L.ptr(ws), ws.numel(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    return mel
+
+
+# --------------------------------------------------------------------------------------------------------- token probs
+def test_token_probs_and_rank(L):
+    g = torch.Generator().manual_seed(2)
+    n, V, eot = 37, 51872, 50257
+    logits = torch.randn(n, V, generator=g) * 3
+    tgt = torch.randint(0, eot, (n,), generator=g)
+    lc = logits.cuda()
+    prob = torch.empty(n, device="cuda")
+    rank = torch.empty(n, dtype=torch.int32, device="cuda")
+    tc = tgt.to(torch.int32).cuda()
+    L.check(L.lib().stb_token_probs(L.ptr(lc), V, n, eot, L.ptr(tc), L.ptr(prob), L.ptr(rank), L.stream_ptr()))
+    torch.cuda.synchronize()
+    p = logits[:, :eot].softmax(-1)
+    ref = p[torch.arange(n), tgt]
+    np.testing.assert_allclose(prob.cpu().numpy(), ref.numpy(), rtol=2e-5)
+    order = p.sort(dim=-1).indices
+    ref_rank = (order == tgt[:, None]).nonzero()[:, -1]
+    assert np.array_equal(rank.cpu().numpy(), ref_rank.numpy())
