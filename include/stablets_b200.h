@@ -165,13 +165,15 @@ STB_API int stb_token_probs(const float* logits, long long ld, int n_rows, int n
                     int32_t* rank_out, void* stream);
 
 /* a5 QK post-processing, legacy alignment-head path (stable_whisper/timing.py:105-110,194):
- *   qk [B][A][M][ldq] fp32 (as written by stb_decoder_forward); rows S..M-2 (R = M-1-S rows), columns [0,F) ->
+ *   qk [B][A][M][ldq] fp32 (as written by stb_decoder_forward; M = rows per head in memory); rows S..S+R-1
+ *   (the reference slices [S:-1], i.e. R = n_text_tokens + 1; smaller R lets windows with fewer tokens share a padded
+ *   decoder batch), columns [0,F) ->
  *   softmax(qk*qk_scale) over columns -> z-norm over the R rows of each column (biased std) -> median filter
  *   (width, reflect) along columns -> mean over the A heads -> matrix [B][R][ldm] fp32.
  *   ws >= stb_qkpost_ws_bytes. */
 STB_API size_t stb_qkpost_ws_bytes(int B, int A, int R, int F);
-STB_API int stb_qk_postprocess(const float* qk, int B, int A, int M, long long ldq, int S, int F, float qk_scale, int medfilt_width,
-                       float* matrix, long long ldm, void* ws, size_t ws_bytes, void* stream);
+STB_API int stb_qk_postprocess(const float* qk, int B, int A, int M, long long ldq, int S, int R, int F, float qk_scale,
+                       int medfilt_width, float* matrix, long long ldm, void* ws, size_t ws_bytes, void* stream);
 
 /* a6 DTW + jump extraction (whisper.timing.dtw CPU semantics + stable_whisper/timing.py:195-198):
  *   x [B][R][ldx] fp32 (cost = -x when negate != 0), path over the R x F grid, strict-'<' tie rule, fp32 cost.

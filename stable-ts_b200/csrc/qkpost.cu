@@ -110,9 +110,9 @@ extern "C" size_t stb_qkpost_ws_bytes(int B, int A, int R, int F) {
     return (size_t)B * A * R * Fp * sizeof(float);
 }
 
-extern "C" int stb_qk_postprocess(const float* qk, int B, int A, int M, long long ldq, int S, int F, float qk_scale,
+extern "C" int stb_qk_postprocess(const float* qk, int B, int A, int M, long long ldq, int S, int R, int F, float qk_scale,
                                   int medfilt_width, float* matrix, long long ldm, void* ws, size_t ws_bytes, void* stream) {
-    const int R = M - 1 - S;
+    STB_REQUIRE(S >= 0 && S + R <= M, "stb_qk_postprocess: rows S=%d R=%d exceed M=%d", S, R, M);
     STB_REQUIRE(qk && matrix && ws, "stb_qk_postprocess: null pointer");
     STB_REQUIRE(R >= 1 && F >= 1 && F <= 1504 && A >= 1 && B >= 1, "stb_qk_postprocess: bad shape R=%d F=%d A=%d B=%d", R, F, A, B);
     STB_REQUIRE(medfilt_width == 7 || medfilt_width == 1, "stb_qk_postprocess: medfilt_width %d unsupported (7 or 1)", medfilt_width);

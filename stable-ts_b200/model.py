@@ -281,15 +281,17 @@ class B200Whisper:
         return prob, rank
 
     # ---- a5 ----
-    def qk_postprocess(self, qk: torch.Tensor, S: int, F: int, qk_scale: float = 1.0, medfilt_width: int = 7) -> torch.Tensor:
-        """qk fp32 [B, A, M, ld] -> matrix fp32 [B, R, F] (R = M-1-S), row pitch rounded to 4."""
+    def qk_postprocess(self, qk: torch.Tensor, S: int, F: int, R: Optional[int] = None, qk_scale: float = 1.0,
+                       medfilt_width: int = 7) -> torch.Tensor:
+        """qk fp32 [B, A, M, ld] -> matrix fp32 [B, R, F]; R defaults to M-1-S (the reference's [S:-1] slice)."""
         B, A, M, ld = qk.shape
-        R = M - 1 - S
+        assert qk.is_contiguous()
+        R = M - 1 - S if R is None else int(R)
         ldm = (F + 3) // 4 * 4
         out = torch.empty(B, R, ldm, dtype=torch.float32, device=self.device)
         ws = self._buf("qkpost", self._lib.stb_qkpost_ws_bytes(B, A, R, F))
-        L.check(self._lib.stb_qk_postprocess(L.ptr(qk), B, A, M, ld, S, F, float(qk_scale), medfilt_width, L.ptr(out), ldm,
-                                             L.ptr(ws), ws.numel(), L.stream_ptr()))
+        L.check(self._lib.stb_qk_postprocess(L.ptr(qk), B, A, M, ld, S, R, F, float(qk_scale), medfilt_width, L.ptr(out),
+                                             ldm, L.ptr(ws), ws.numel(), L.stream_ptr()))
         return out[:, :, :F]
 
     # ---- a6 ----

@@ -1,0 +1,276 @@
+"""Host-side mirror of stable_whisper/timing.py for the B200 path.
+
+Same names, argument meaning and error behaviour as the reference (``WordTiming``, ``find_alignment_stable``,
+``split_word_tokens``, ``pop_empty_alignment``, ``add_word_timestamps_stable``), but the per-window math is the
+batched kernel pipeline of libstablets_b200.so:
+
+    log-mel -> encoder -> cross K/V -> teacher-forced decoder (+QK capture of the alignment heads) -> token probs
+    -> QK post-processing -> DTW (+jump extraction)                       [stable_whisper/timing.py:41-198]
+
+Only the bookkeeping that the reference keeps in Python (word/token grouping, gap padding, punctuation merge,
+rounding) runs on the host.  Windows are independent here, so ``align_windows``
+takes a LIST of windows and runs them as one batch (the reference is batch 1, timing.py:60-61).
+"""
+import string
+from dataclasses import dataclass
+from itertools import chain
+from typing import Callable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .model import B200Whisper
+
+N_SAMPLES = 480000
+N_SAMPLES_PER_TOKEN = 320
+TOKENS_PER_SECOND = 50
+
+
+@dataclass
+class WordTiming:          # stable_whisper/timing.py:22-28
+    word: str
+    tokens: List[int]
+    start: float
+    end: float
+    probability: float
+
+
+@dataclass
+class WindowJob:
+    """One <=30 s window: audio (fp32, 16 kHz, <=480000 samples) or a mel / encoder output, plus its token script."""
+    text_tokens: List[int]
+    num_samples: int
+    audio: Optional[torch.Tensor] = None
+
+
+def n_frames_for(num_samples: int) -> int:
+    return round(num_samples / N_SAMPLES_PER_TOKEN)     # Python banker's rounding, as timing.py:88,106
+
+
+def token_row(tokenizer, text_tokens: Sequence[int]) -> List[int]:
+    return [*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot]
+
+
+def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, enc=None, heads=None,
+                         want_logits: bool = True):
+    """Device side of ``_compute_qks`` for a batch of windows.  Returns dict(enc, ckv, logits, qk, M, S, rows)."""
+    B = len(jobs)
+    if enc is None:
+        audio = torch.zeros(B, N_SAMPLES, dtype=torch.float32)
+        for i, j in enumerate(jobs):
+            a = j.audio.detach().float().flatten()[:N_SAMPLES]
+            audio[i, : a.numel()] = a
+        audio = audio.pin_memory().to(model.device, non_blocking=True)
+        mel = model.log_mel(audio)                         # == log_mel_spectrogram(audio, padding=N_SAMPLES-n)
+        enc = model.encode(mel)
+    ckv = model.cross_kv(enc)
+    S = len(tokenizer.sot_sequence)
+    rows = [token_row(tokenizer, j.text_tokens) for j in jobs]
+    M = max(len(r) for r in rows)
+    tok = torch.full((B, M), int(tokenizer.eot), dtype=torch.int32)
+    for i, r in enumerate(rows):
+        tok[i, : len(r)] = torch.tensor(r, dtype=torch.int32)
+    logits, qk = model.decode_forced(tok, ckv, want_logits=want_logits,
+                                     heads=model.alignment_head_pairs if heads is None else heads)
+    return dict(enc=enc, ckv=ckv, logits=logits, qk=qk, M=M, S=S, rows=rows)
+
+
+def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfilt_width: int = 7, qk_scale: float = 1.0,
+                  enc=None, return_intermediates: bool = False):
+    """Batched equivalent of ``_compute_jump_indices`` (legacy alignment-head path).
+
+    -> list (per window) of (jump_indices int array [N+1], text_token_probs list[N]) (+ intermediates).
+    """
+    fw = window_batch_forward(model, tokenizer, jobs, enc=enc)
+    S, logits, qk = fw["S"], fw["logits"], fw["qk"]
+    out, inter = [], []
+    # windows with the same (N, F) share one post-processing / DTW launch
+    groups = {}
+    for i, j in enumerate(jobs):
+        groups.setdefault((len(j.text_tokens), n_frames_for(j.num_samples)), []).append(i)
+    results = [None] * len(jobs)
+    for (N, F), idx in groups.items():
+        sel = torch.tensor(idx, device=model.device)
+        qk_g = qk if len(idx) == len(jobs) else qk.index_select(0, sel).contiguous()
+        matrix = model.qk_postprocess(qk_g, S, F, R=N + 1, qk_scale=qk_scale, medfilt_width=medfilt_width)
+        jumps = model.dtw(matrix, negate=True)
+        tgt = torch.tensor([jobs[i].text_tokens for i in idx], dtype=torch.int32).reshape(-1)
+        rows = torch.cat([logits[i, S:S + N] for i in idx]) if N > 0 else logits[:0, 0]
+        probs, _ = model.token_probs(rows, tokenizer.eot, tgt) if N > 0 else (torch.empty(0), None)
+        jumps_h = jumps.cpu().numpy()
+        probs_h = probs.cpu().numpy().astype(np.float64).reshape(len(idx), N)
+        for k, i in enumerate(idx):
+            results[i] = (jumps_h[k].astype(np.int64), probs_h[k].tolist())
+            if return_intermediates:
+                inter.append((i, matrix[k].cpu()))
+    if return_intermediates:
+        inter = [m for _, m in sorted(inter, key=lambda t: t[0])]
+        return results, dict(forward=fw, matrices=inter)
+    return results
+
+
+def word_timings_from_jumps(jumps: np.ndarray, token_probs: List[float], words, word_tokens) -> List[WordTiming]:
+    """stable_whisper/timing.py:251-253,289-306; ``word_tokens`` already ends with the [eot] pseudo-word."""
+    wb = np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0))
+    jump_times = jumps / TOKENS_PER_SECOND
+    starts, ends = jump_times[wb[:-1]], jump_times[wb[1:]]
+    probs = [np.mean(token_probs[i:j]) for i, j in zip(wb[:-1], wb[1:])]
+    return [WordTiming(w, t, s, e, p) for w, t, s, e, p in zip(words, word_tokens, starts, ends, probs)]
+
+
+def find_alignment_stable(model: B200Whisper, tokenizer, text_tokens: List[int], audio: Optional[torch.Tensor],
+                          num_samples: int, *, medfilt_width: int = 7, qk_scale: float = 1.0, token_split=None,
+                          enc=None, dynamic_heads=None, aligner: Union[str, dict] = "legacy", extra_models=None,
+                          ts_num: int = 0, ts_noise=None) -> List[WordTiming]:
+    """One window (stable_whisper/timing.py:202-306).  ``audio`` replaces ``mel`` (the log-mel runs on the device)."""
+    if extra_models:
+        raise NotImplementedError("extra_models is not supported by the B200 path yet")
+    if dynamic_heads or aligner != "legacy":
+        raise NotImplementedError("only the legacy alignment-head aligner runs on the B200 path in this round")
+    if token_split is None:
+        words, word_tokens = tokenizer.split_to_word_tokens(list(text_tokens) + [tokenizer.eot])
+    else:
+        words, word_tokens = token_split
+        words = list(words) + [tokenizer.decode([tokenizer.eot])]
+        word_tokens = list(word_tokens) + [[tokenizer.eot]]
+    job = WindowJob(list(text_tokens), num_samples, audio)
+    (jumps, probs), = align_windows(model, tokenizer, [job], medfilt_width=medfilt_width, qk_scale=qk_scale, enc=enc)
+    return word_timings_from_jumps(jumps, probs, words, word_tokens)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# bookkeeping the reference keeps on the host
+# ---------------------------------------------------------------------------------------------------------
+def _split_tokens(tokens: List[int], tokenizer):
+    """Group tokens into words by incremental decoding (stable_whisper/timing.py:309-341)."""
+    lang = getattr(tokenizer, "language_code", getattr(tokenizer, "language", None))
+    by_space = lang not in {"zh", "ja", "th", "lo", "my"}
+    remaining = tokenizer.decode_with_timestamps(tokens)
+    words, groups, cur = [], [], []
+    append_to_prev = False
+    cur_text = ""
+    for tok in tokens:
+        cur.append(tok)
+        cur_text = tokenizer.decode(cur)
+        whole = tok >= tokenizer.eot
+        if not whole:
+            whole = remaining[: len(cur_text)] == cur_text
+            if whole and by_space:
+                append_to_prev = not (cur_text.startswith(" ") or cur_text.strip() in string.punctuation)
+        if whole:
+            if append_to_prev and words:
+                words[-1] += cur_text
+                groups[-1].extend(cur)
+            else:
+                words.append(cur_text)
+                groups.append(cur)
+            remaining = remaining[len(cur_text):]
+            cur = []
+    if cur:
+        words.append(cur_text if len(remaining) == 0 else remaining)
+        groups.append(cur)
+    elif remaining:
+        words[-1] += remaining
+    return words, groups
+
+
+def split_word_tokens(segments: List[dict], tokenizer, *, padding: Union[str, int, None] = None,
+                      split_callback: Optional[Callable] = None, pad_first_seg: bool = True):
+    """stable_whisper/timing.py:344-392 (char_split is part of the 'new' aligner and not mirrored)."""
+    if padding is not None:
+        padding = tokenizer.encode(padding) if isinstance(padding, str) else [padding]
+    tokens, seg_indices, words, word_tokens = [], [], [], []
+    for i, seg in enumerate(segments):
+        text_toks = [t for t in seg["tokens"] if not isinstance(t, int) or t < tokenizer.eot]
+        cw, cwt = _split_tokens(text_toks, tokenizer) if split_callback is None else split_callback(text_toks, tokenizer)
+        assert len(cw) == len(cwt), f"word count and token group count do not match, {len(cw)} and {len(cwt)}"
+        if (padding is not None and cwt[0][0] != padding and (len(tokens) == 0 or tokens[-1] != padding)
+                and (pad_first_seg or i != 0)):
+            tokens.extend(padding)
+            words.append(None)
+            word_tokens.append(padding)
+        seg_indices.extend([i] * len(cw))
+        tokens.extend(chain.from_iterable(cwt))
+        words.extend(cw)
+        word_tokens.extend(cwt)
+    return tokens, (words, word_tokens), seg_indices
+
+
+def pop_empty_alignment(alignment: List[WordTiming], seg_indices: Optional[List[int]] = None):
+    """Remove the gap-padding pseudo-words (word is None); stable_whisper/timing.py:395-407."""
+    if seg_indices is None:
+        kept = [a for a in alignment if a.word is None]
+        alignment[:] = [a for a in alignment if a.word is not None]
+        return kept
+    pos = len(seg_indices)
+    popped = {}
+    for i in reversed(range(len(alignment))):
+        assert pos != -1
+        if alignment[i].word is None:
+            popped[seg_indices[pos]] = alignment.pop(i)
+        else:
+            pos -= 1
+    return popped
+
+
+def merge_punctuations(alignment: List[WordTiming], prepended: str, appended: str):
+    """whisper.timing.merge_punctuations semantics."""
+    i, j = len(alignment) - 2, len(alignment) - 1
+    while i >= 0:
+        prev, nxt = alignment[i], alignment[j]
+        if prev.word.startswith(" ") and prev.word.strip() in prepended:
+            nxt.word, nxt.tokens = prev.word + nxt.word, prev.tokens + nxt.tokens
+            prev.word, prev.tokens = "", []
+        else:
+            j = i
+        i -= 1
+    i, j = 0, 1
+    while j < len(alignment):
+        prev, nxt = alignment[i], alignment[j]
+        if not prev.word.endswith(" ") and nxt.word in appended:
+            prev.word, prev.tokens = prev.word + nxt.word, prev.tokens + nxt.tokens
+            nxt.word, nxt.tokens = "", []
+        else:
+            i = j
+        j += 1
+
+
+PREPEND_PUNCT = "\"'“¿([{-"
+APPEND_PUNCT = "\"'.。,，!！?？:：”)]}、"
+
+
+def add_word_timestamps_stable(*, segments: List[dict], model: B200Whisper, tokenizer, audio: Optional[torch.Tensor] = None,
+                               num_samples: int, prepend_punctuations: Optional[str] = PREPEND_PUNCT,
+                               append_punctuations: Optional[str] = APPEND_PUNCT, enc=None, min_word_dur: float = 0.1,
+                               split_callback: Optional[Callable] = None, gap_padding: Optional[str] = " ...",
+                               pad_first_seg: bool = True, aligner="legacy", **kwargs):
+    """Mutates ``segments[i]['words'|'start'|'end']`` in place (stable_whisper/timing.py:411-500)."""
+    if len(segments) == 0:
+        return
+    min_word_dur = min_word_dur or 0
+    prepend_punctuations = PREPEND_PUNCT if prepend_punctuations is None else prepend_punctuations
+    append_punctuations = APPEND_PUNCT if append_punctuations is None else append_punctuations
+    for seg in segments:
+        seg["words"] = []
+    text_tokens, token_split, seg_indices = split_word_tokens(segments, tokenizer, padding=gap_padding,
+                                                              split_callback=split_callback, pad_first_seg=pad_first_seg)
+    alignment = find_alignment_stable(model, tokenizer, text_tokens, audio, num_samples, token_split=token_split, enc=enc,
+                                      aligner=aligner, **kwargs)
+    alt_begin = pop_empty_alignment(alignment, seg_indices)
+    merge_punctuations(alignment, prepend_punctuations, append_punctuations)
+    offset = segments[0]["seek"]
+    assert len(alignment) == len(seg_indices)
+    assert gap_padding is None or len(segments) == len(alt_begin) + (1, 0)[pad_first_seg]
+    for i, timing in zip(seg_indices, alignment):
+        if len(timing.tokens) == 0:
+            continue
+        start, end = timing.start, timing.end
+        if len(segments[i]["words"]) == 0 and (end - start) < min_word_dur and i in alt_begin:
+            start = alt_begin[i].start
+        segments[i]["words"].append(dict(word=timing.word, start=round(offset + start, 3), end=round(offset + end, 3),
+                                         probability=timing.probability, tokens=timing.tokens))
+    for seg in segments:
+        if seg["words"]:
+            seg["start"] = seg["words"][0]["start"]
+            seg["end"] = seg["words"][-1]["end"]

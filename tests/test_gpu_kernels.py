@@ -222,7 +222,7 @@ def test_qk_postprocess_vs_oracle(L, A, M, F, S):
     out = torch.empty(Bn, R, ldm, device="cuda")
     ws = torch.empty(lib.stb_qkpost_ws_bytes(Bn, A, R, F), dtype=torch.uint8, device="cuda")
     qkc = qk.cuda()
-    L.check(lib.stb_qk_postprocess(L.ptr(qkc), Bn, A, M, 1504, S, F, 1.0, 7, L.ptr(out), ldm, L.ptr(ws), ws.numel(),
+    L.check(lib.stb_qk_postprocess(L.ptr(qkc), Bn, A, M, 1504, S, R, F, 1.0, 7, L.ptr(out), ldm, L.ptr(ws), ws.numel(),
                                    L.stream_ptr()))
     torch.cuda.synchronize()
     for b in range(Bn):
