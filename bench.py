@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric (real-time factor + aligned words/s, Whisper large-v3, 30 s windows) on
+N B200s of one node.
+
+    python bench.py [--gpus N --steps K --warmup W]              # this repo's B200 path (N>1: launched by torchrun)
+    python bench.py --impl reference [...]                       # the reference's CPU path (oracle port) on host cores
+
+One "step" = one pass of the hot path over one batch of synthetic 30 s windows per GPU:
+    log-mel -> encoder -> cross K/V -> teacher-forced decoder with cross-attention capture -> token probabilities
+    -> QK post-processing -> DTW -> word timings            (stable_whisper `align` per-window math)
+`value` times the device pipeline with inputs resident in HBM (CUDA events); `e2e` times the public API call
+(`stable_ts_b200.alignment.align_words_batch`) from pinned HOST audio to host word lists, including the final
+all-gather of word records when N > 1.  Weights are seeded random init at the true large-v3 shapes (no checkpoints
+offline); token scripts are seeded synthetic ids.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+AUDIO_S = 30.0
+N_SAMPLES = 480000
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--model", default="large-v3")
+    p.add_argument("--windows", type=int, default=16, help="30 s windows per GPU per step")
+    p.add_argument("--tokens", type=int, default=100, help="text tokens per window (reference align token_step)")
+    p.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
+    p.add_argument("--cpu-windows", type=int, default=1, help="windows in the bounded CPU-baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--ncu", action="store_true", help="profiling run: warm up, then ONE step inside cudaProfilerStart/Stop")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------- synthetic workload
+def synth_audio(n_samples: int, seed: int) -> torch.Tensor:
+    """AM-modulated sinusoids + noise, peak 0.3; same recipe as the oracle's generator."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n_samples, dtype=torch.float64) / 16000
+    k = int(torch.randint(3, 6, (1,), generator=g))
+    x = torch.zeros(n_samples, dtype=torch.float64)
+    for _ in range(k):
+        f = 100 + 3900 * float(torch.rand(1, generator=g))
+        fm = 2 + 6 * float(torch.rand(1, generator=g))
+        ph = 2 * np.pi * float(torch.rand(1, generator=g))
+        x += torch.sin(2 * np.pi * f * t + ph) * (0.5 + 0.5 * torch.sin(2 * np.pi * fm * t))
+    x += 0.01 * torch.randn(n_samples, generator=g, dtype=torch.float64)
+    return (0.3 * x / x.abs().max()).float()
+
+
+def make_windows(n, n_tokens, eot, seed0):
+    audios, word_tokens = [], []
+    for i in range(n):
+        audios.append(synth_audio(N_SAMPLES, seed0 + i))
+        g = torch.Generator().manual_seed(4321 + seed0 + i)
+        script = torch.randint(256, eot, (n_tokens,), generator=g).tolist()
+        wts, j = [], 0
+        while j < n_tokens:                               # synthetic "words" of 1-3 tokens
+            k = int(torch.randint(1, 4, (1,), generator=g))
+            wts.append(script[j:j + k])
+            j += k
+        word_tokens.append(wts)
+    return audios, word_tokens
+
+
+def algorithmic_flops_per_window(d, n_tokens, S):
+    """encoder + teacher-forced decoder FLOPs of one 30 s window."""
+    T, M = 1500, S + n_tokens + 2
+    dm, L, V, C = d.n_audio_state, d.n_audio_layer, d.n_vocab, d.n_mels
+    enc = 2 * 3000 * 3 * C * dm + 2 * 1500 * 3 * dm * dm + L * (24 * T * dm * dm + 4 * T * T * dm)
+    dt, Ld = d.n_text_state, d.n_text_layer
+    dec = Ld * (28 * M * dt * dt + 4 * M * M * dt + 4 * T * dt * dt + 4 * M * T * dt) + 2 * M * dt * V
+    return float(enc + dec)
+
+
+# ------------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU arm
+_CPU = {}
+
+
+def host_cores() -> int:
+    """Cores this process may actually use: min(affinity mask, cgroup CPU quota).  os.cpu_count() reports the whole
+    host and oversubscribes badly inside a quota-limited container."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+def cpu_arm(args, dims_tuple, n_windows, threads=None):
+    """The reference's CPU path for the same workload: oracle port (oracle/ = restated openai-whisper + stable-ts
+    orchestration, fp32, PyTorch CPU with all host threads).  Returns (audio_s_per_s, words_per_s, seconds, cores).
+    Model construction is outside the timed region (as for the GPU arm)."""
+    import oracle.whisper_ref as W
+    from oracle import stable_path as SP
+    from stable_ts_b200.api import random_state_dict
+    from stable_ts_b200.model import ModelDimensions
+    cores = threads or host_cores()
+    torch.set_num_threads(cores)
+    if "model" not in _CPU:
+        model = W.Whisper(W.ModelDimensions(*dims_tuple)).eval()
+        model.load_state_dict(random_state_dict(ModelDimensions(*dims_tuple), seed=0))
+        tk = W.tokenizer.get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language="en",
+                                       task="transcribe")
+        _CPU.update(model=model, tk=tk, data=make_windows(n_windows, args.tokens, tk.eot, seed0=1000))
+    model, tk = _CPU["model"], _CPU["tk"]
+    audios, wts = _CPU["data"]
+    t0 = time.perf_counter()
+    n_words = 0
+    for a, wt in zip(audios, wts):
+        n_words += len(SP.align_audio_window(model, tk, wt, a))
+    dt = time.perf_counter() - t0
+    return n_windows * AUDIO_S / dt, n_words / dt, dt, cores
+
+
+def run_reference(args, dims_tuple):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return                                     # only rank 0 runs the CPU arm
+    per_step = []
+    words = 0.0
+    for i in range(args.warmup + args.steps):
+        v, w, dt, cores = cpu_arm(args, dims_tuple, args.cpu_windows)
+        if i >= args.warmup:
+            per_step.append(dt)
+            words = w
+        if sum(per_step) > 240:                    # bounded: stop early, report the steps that ran
+            break
+    dt = statistics.mean(per_step)
+    value = args.cpu_windows * AUDIO_S / dt
+    out = {
+        "impl": "reference", "metric": f"rtfx_{args.model}_align", "value": value, "unit": "audio_s/s", "n_gpus": args.gpus,
+        "steps": len(per_step), "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"align {args.model}, {args.cpu_windows} window(s) of 30 s per step, {args.tokens} tokens/window",
+                   "weights": "seeded random init"},
+        "aligned_words_per_s": words, "rtf": 1.0 / value,
+        "cpu_baseline": {"value": value, "unit": "audio_s/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.cpu_windows} window(s) x {len(per_step)} step(s), oracle port of the reference CPU path"},
+        "e2e": {"value": value, "unit": "audio_s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- B200 arm
+def run_b200(args, dims_tuple):
+    import torch.distributed as dist
+    from stable_ts_b200 import _lib as L
+    from stable_ts_b200.alignment import align_words_batch
+    from stable_ts_b200.api import load_model
+    from stable_ts_b200.timing import WindowJob, align_windows
+    from stable_ts_b200.tokenizer import get_tokenizer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    lib = L.lib()
+
+    model = load_model(args.model, device=dev, precision=args.precision, seed=0)
+    tk = get_tokenizer(model, language="en", task="transcribe", synthetic=True)
+    S = len(tk.sot_sequence)
+    Wn = args.windows
+    pools = 2                                           # rotate distinct inputs between steps
+    batches = [make_windows(Wn, args.tokens, tk.eot, seed0=1000 + 100000 * rank + 1000 * p) for p in range(pools)]
+    n_words_step = sum(len(w) for w in batches[0][1])
+    host_audio = [torch.stack(b[0]).pin_memory() for b in batches]
+    dev_audio = [h.to(dev) for h in host_audio]
+    jobs = [[WindowJob([t for w in wt for t in w], N_SAMPLES, None) for wt in b[1]] for b in batches]
+
+    def device_step(p):
+        """hot path with inputs resident in HBM; results stay on the device except the tiny jumps/probs read-back"""
+        mel = model.log_mel(dev_audio[p])
+        enc = model.encode(mel)
+        return align_windows(model, tk, jobs[p], enc=enc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-timed
+    for i in range(args.warmup):
+        device_step(i % pools)
+    barrier()
+    if args.ncu:                                        # `ncu --profile-from-start off ... bench.py --ncu`
+        torch.cuda.profiler.start()
+        device_step(0)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = lib.stb_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        device_step(i % pools)
+    e1.record()
+    barrier()
+    launches = (lib.stb_launch_count() - l0) // max(args.steps, 1)
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    value = world * Wn * AUDIO_S / (ms_step / 1e3)
+
+    # ---- e2e: public API with host buffers (+ the one gather of word records when N > 1)
+    def e2e_step(p):
+        res = align_words_batch(model, tk, list(host_audio[p]), batches[p][1])
+        rec = torch.tensor([[w["start"], w["end"], w["probability"]] for r in res for w in r], dtype=torch.float32)
+        if world > 1:
+            out = [torch.empty_like(rec, device=dev) for _ in range(world)]
+            dist.all_gather(out, rec.to(dev))
+            rec = torch.cat(out).cpu()
+        return rec
+
+    for i in range(max(1, min(args.warmup, 2))):
+        e2e_step(i % pools)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        e2e_step(i % pools)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_value = world * Wn * AUDIO_S / e2e_s
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM core): per-launch CUDA events on the launching stream
+    lib.stb_prof_enable(1)
+    device_step(0)
+    import ctypes
+    g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    L.check(lib.stb_prof_collect(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n)))
+    lib.stb_prof_enable(0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    achieved_tf = g_fl.value / (g_ms.value * 1e-3) / 1e12 if g_ms.value > 0 else 0.0
+    passes = 3 if args.precision == "fp16x3" else 1
+    roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::f16, TMA-fed)", "achieved": achieved_tf,
+            "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s (of fallback)",
+            "traffic": None,
+            "note": f"achieved = algorithmic fp32-grade GEMM FLOPs / event-timed GEMM time; each is executed as {passes} fp16 "
+                    f"tensor-core pass(es), i.e. tensor-pipe rate = {achieved_tf * passes:.1f} TFLOP/s",
+            "gemm_launches_per_step": int(g_n.value), "gemm_ms_per_step": g_ms.value,
+            "gemm_share_of_step": g_ms.value / ms_step if ms_step > 0 else None,
+            "algorithmic_gflop_per_window": algorithmic_flops_per_window(model.dims, args.tokens, S) / 1e9}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        v, w, dt, cores = cpu_arm(args, dims_tuple, args.cpu_windows)
+        cpu = {"value": v, "unit": "audio_s/s", "cores": cores, "kind": "port", "aligned_words_per_s": w,
+               "sample": f"{args.cpu_windows} window(s) of the same workload ({dt:.1f} s of CPU work), oracle port of the "
+                         f"reference CPU path, fp32, torch threads = {cores}"}
+    out = {
+        "metric": f"rtfx_{args.model}_align", "value": value, "unit": "audio_s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16 x3 split (fp32-grade), fp32 accumulate" if args.precision == "fp16x3" else "f16, fp32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": f"align {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} text tokens/window "
+                               f"(config 3 shape at the metric's model)",
+                   "weights": "seeded random init at true shapes", "precision": args.precision,
+                   "l2": "per-step working set (weights 6.2 GB + activations) >> 126 MB L2; inputs rotate between 2 pools"},
+        "rtf": 1.0 / value, "aligned_words_per_s": world * n_words_step / (ms_step / 1e3),
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "audio_s/s", "h2d_bytes_per_step": Wn * N_SAMPLES * 4,
+                "d2h_bytes_per_step": int(Wn * (args.tokens + 1) * 4 + Wn * args.tokens * 4), "ms_per_step": e2e_s * 1e3,
+                "aligned_words_per_s": world * n_words_step / e2e_s},
+    }
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    from stable_ts_b200.api import MODEL_DIMS
+    dims_tuple = MODEL_DIMS[args.model]
+    if args.impl == "reference":
+        run_reference(args, dims_tuple)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback); use --impl reference for the CPU arm")
+        run_b200(args, dims_tuple)
+
+
+if __name__ == "__main__":
+    main()

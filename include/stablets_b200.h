@@ -43,6 +43,10 @@ extern "C" {
 
 STB_API const char* stb_last_error(void);
 STB_API int stb_abi_version(void);
+/* measurement hooks (bench.py): kernels launched by this library so far; per-launch CUDA-event timing of the GEMM core */
+STB_API unsigned long long stb_launch_count(void);
+STB_API void stb_prof_enable(int on);
+STB_API int stb_prof_collect(double* gemm_ms, double* gemm_flops, long long* gemm_launches);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a1  log-mel front-end.  Replaces whisper.audio.log_mel_spectrogram + pad_or_trim

@@ -42,6 +42,9 @@ class Dims(ctypes.Structure):
 _SIGS = {
     "stb_last_error": (c_char_p, []),
     "stb_abi_version": (c_int, []),
+    "stb_launch_count": (ctypes.c_ulonglong, []),
+    "stb_prof_enable": (None, [c_int]),
+    "stb_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_longlong)]),
     "stb_logmel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                            c_size_t, c_void_p]),
     "stb_gemm": (c_int, [POINTER(Operand), POINTER(Operand), c_int, c_int, POINTER(Epilogue), c_void_p]),

@@ -36,6 +36,7 @@ const char* get_error();
 
 #define STB_LAUNCH_OK()                                                                                \
     do {                                                                                               \
+        stb::count_launch();                                                                           \
         cudaError_t e__ = cudaGetLastError();                                                          \
         if (e__ != cudaSuccess) {                                                                      \
             stb::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(e__));  \
@@ -51,6 +52,7 @@ const char* get_error();
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+void count_launch();   // every kernel launch of this library bumps the counter read by stb_launch_count()
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 
 #ifdef __CUDACC__

@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 namespace stb {
+unsigned long long launches();
 
 static thread_local char g_err[1024] = "";
 
@@ -15,6 +16,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 const char* get_error() { return g_err; }
+
+static unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+unsigned long long launches() { return g_launches; }
 
 int sm_count() {
     static int n = 0;
@@ -45,6 +50,7 @@ __global__ void split_f16_kernel(const float* __restrict__ src, long long rows, 
 
 extern "C" const char* stb_last_error(void) { return stb::get_error(); }
 extern "C" int stb_abi_version(void) { return 1; }
+extern "C" unsigned long long stb_launch_count(void) { return stb::launches(); }
 
 extern "C" int stb_split_f16(const float* src, long long rows, int cols, long long src_ld, void* hi, void* lo,
                              long long dst_ld, void* stream) {
