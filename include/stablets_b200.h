@@ -187,22 +187,39 @@ STB_API size_t stb_dtw_smem_bytes(int R, int F);
 STB_API int stb_dtw(const float* x, int B, int R, int F, long long ldx, int negate, int32_t* jumps, int32_t* path,
             int32_t* path_len, void* stream);
 
-/* a9 KV-cached decode step(s): see stb_decode_* in the section below (decode.py:33-65). */
+/* a9 KV-cached decode (stable_whisper/decode.py:33-65; whisper PyTorchInference.logits + logit filters +
+ *    GreedyDecoder.update).  One step = one decoder forward for the newest token of B sequences.
+ *    Everything position-dependent is read from the DEVICE counter `pos` (index of the token being fed), which the step
+ *    increments at its end, so a single captured CUDA graph can replay every step.
+ *    state: self-attention K/V caches fp32 [L][2][B][n_text_ctx][d] (stb_decode_state_bytes).
+ *    tokens_in [B] int32 -> logits_out [B][ld_logits] fp32. */
 STB_API size_t stb_decode_state_bytes(const stb_model* m, int B);
 STB_API size_t stb_decode_ws_bytes(const stb_model* m, int B);
-/* One decoder step for B sequences at position `pos` (0-based index of the token being fed):
- *   tokens_in [B] int32 -> logits_out [B][ld_logits] fp32.  self-attention K/V are appended to `state`. */
-STB_API int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int pos, const void* cross_kv, void* state,
+STB_API int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const void* cross_kv, void* state,
                     float* logits_out, long long ld_logits, void* ws, size_t ws_bytes, void* stream);
-/* Logit filters + greedy pick for one step (decode.py:46-58 + whisper.decoding filters), in place on logits:
- *   suppress_mask [V] uint8 (1 = -inf; SuppressTokens/SuppressBlank resolved by the host for this step),
- *   ts_mask (nullable) [1501] uint8 silent-timestamp mask, timestamp rules from the per-sequence state
- *   last_ts[B] (last timestamp token seen or -1), last_was_ts[B], penult_was_ts[B] (uint8),
- *   is_first_step, max_initial_ts (or -1).  next_out [B] int32 = argmax (first max index), logprob_out [B] fp32. */
+
+/* per-sequence sampling state kept on the device */
+typedef struct {
+    int32_t n_sampled;   /* tokens sampled so far (0 at sample_begin) */
+    int32_t last_tok;    /* newest sampled token */
+    int32_t prev_tok;    /* the one before */
+    int32_t last_ts;     /* most recent timestamp token sampled, or -1 */
+    int32_t done;        /* newest token is EOT */
+    float sum_logprob;   /* GreedyDecoder.sum_logprobs */
+} stb_seq_state;
+
+/* Logit filters + greedy pick for one step, in place on logits [B][ld] (decode.py:46-58 + whisper.decoding filters):
+ *   suppress_mask [V] uint8 (SuppressTokens), first_step_mask [V] uint8 applied when n_sampled == 0 (SuppressBlank),
+ *   ApplyTimestampRules from the per-sequence state (apply_ts_rules, no_timestamps id, max_initial_ts index or -1),
+ *   ts_mask (nullable) [1501] uint8 silent-timestamp mask, NaN -> -inf, argmax (first max index), log-softmax gather,
+ *   sum_logprob += logprob unless the sequence already ended, ended sequences keep emitting EOT.
+ *   Step tables (nullable, [table_rows][B] int32, row = n_sampled so no per-step host traffic is needed):
+ *   forced_table: token appended instead of the argmax (fixed-length benchmark scripts / teacher forcing);
+ *   token_table: the appended token; argmax_table: the argmax before forcing.  next_out [B] feeds stb_decode_step. */
 STB_API int stb_sample_greedy(float* logits, long long ld, int B, int V, int eot, int ts_begin, int no_timestamps,
-                      const uint8_t* suppress_mask, const uint8_t* ts_mask, const int32_t* last_ts,
-                      const uint8_t* last_was_ts, const uint8_t* penult_was_ts, int is_first_step, int max_initial_ts,
-                      int apply_ts_rules, int32_t* next_out, float* logprob_out, void* stream);
+                      const uint8_t* suppress_mask, const uint8_t* first_step_mask, const uint8_t* ts_mask,
+                      int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
+                      int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows, void* stream);
 
 #ifdef __cplusplus
 }

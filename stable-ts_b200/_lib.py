@@ -63,6 +63,12 @@ _SIGS = {
     "stb_qkpost_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "stb_qk_postprocess": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_float, c_int, c_void_p,
                                    c_longlong, c_void_p, c_size_t, c_void_p]),
+    "stb_decode_state_bytes": (c_size_t, [c_void_p, c_int]),
+    "stb_decode_ws_bytes": (c_size_t, [c_void_p, c_int]),
+    "stb_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p,
+                                c_size_t, c_void_p]),
+    "stb_sample_greedy": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "stb_dtw_smem_bytes": (c_size_t, [c_int, c_int]),
     "stb_dtw": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -373,6 +373,73 @@ static int decoder_forward(stb_model* m, const int32_t* tokens, int B, int M, co
     return STB_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// KV-cached decode step
+// ---------------------------------------------------------------------------------------------------------
+struct StepWs {
+    float* x;
+    float* qkv;
+    float* q;
+    Split ln, attn, hid;
+    size_t bytes;
+};
+static StepWs carve_step(const stb_model* m, int B, void* ws) {
+    const bool lo = m->prec == STB_PREC_FP16X3;
+    const size_t d = m->dims.n_text_state;
+    Carver c(ws);
+    StepWs w;
+    w.x = c.take<float>((size_t)B * d);
+    w.qkv = c.take<float>((size_t)B * 3 * d);
+    w.q = c.take<float>((size_t)B * d);
+    w.ln = take_split(c, (size_t)B * d, lo);
+    w.attn = take_split(c, (size_t)B * d, lo);
+    w.hid = take_split(c, (size_t)B * 4 * d, lo);
+    w.bytes = c.off;
+    return w;
+}
+static size_t decode_state_bytes(const stb_model* m, int B) {
+    return (size_t)m->dims.n_text_layer * 2 * B * m->dims.n_text_ctx * m->dims.n_text_state * sizeof(float);
+}
+
+static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos, const void* ckv, void* state, float* logits,
+                       long long ld_logits, void* ws, cudaStream_t st) {
+    const stb_dims& D = m->dims;
+    const int d = D.n_text_state, H = D.n_text_head, ctx = D.n_text_ctx;
+    const void* const(*t)[2] = m->t;
+    StepWs w = carve_step(m, B, ws);
+    const size_t cache = (size_t)B * ctx * d;
+    STB_TRY(embed_step(tokens, pos, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
+    for (int l = 0; l < D.n_text_layer; ++l) {
+        const stb_model::Layer& L = m->dec[l];
+        float* Kc = (float*)state + (size_t)l * 2 * cache;
+        float* Vc = Kc + cache;
+        STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_ATTN_LN_G), W_F32(L, STB_L_ATTN_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
+        STB_TRY(linear(m, w.ln, B, d, W_HI(L, STB_L_QKV_W), W_LO(L, STB_L_QKV_W), 3 * d,
+                       ep_f32(w.qkv, 3 * d, W_F32(L, STB_L_QKV_B), nullptr, 0), st));
+        STB_TRY(decode_attn_self(w.qkv, Kc, Vc, B, H, d, ctx, pos, w.attn.hi, w.attn.lo, st));
+        STB_TRY(linear(m, w.attn, B, d, W_HI(L, STB_L_OUT_W), W_LO(L, STB_L_OUT_W), d,
+                       ep_f32(w.x, d, W_F32(L, STB_L_OUT_B), w.x, d), st));
+        STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_CROSS_LN_G), W_F32(L, STB_L_CROSS_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
+        STB_TRY(linear(m, w.ln, B, d, W_HI(L, STB_L_CQ_W), W_LO(L, STB_L_CQ_W), d,
+                       ep_f32(w.q, d, W_F32(L, STB_L_CQ_B), nullptr, 0), st));
+        Split Kx, vTx;
+        cross_ptrs(m, B, ckv, l, Kx, vTx);
+        STB_TRY(decode_attn_cross(w.q, Kx.hi, Kx.lo, vTx.hi, vTx.lo, B, H, d, w.attn.hi, w.attn.lo, st));
+        STB_TRY(linear(m, w.attn, B, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d,
+                       ep_f32(w.x, d, W_F32(L, STB_L_COUT_B), w.x, d), st));
+        STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
+        STB_TRY(linear(m, w.ln, B, d, W_HI(L, STB_L_FC1_W), W_LO(L, STB_L_FC1_W), 4 * d,
+                       ep_split(w.hid, 4 * d, W_F32(L, STB_L_FC1_B), STB_ACT_GELU), st));
+        STB_TRY(linear(m, w.hid, B, 4 * d, W_HI(L, STB_L_FC2_W), W_LO(L, STB_L_FC2_W), d,
+                       ep_f32(w.x, d, W_F32(L, STB_L_FC2_B), w.x, d), st));
+    }
+    STB_TRY(layernorm(w.x, B, d, (const float*)t[STB_T_DEC_LN_G][0], (const float*)t[STB_T_DEC_LN_B][0], w.ln.hi, w.ln.lo, nullptr, st));
+    STB_TRY(linear(m, w.ln, B, d, t[STB_T_DEC_TOKEMB][0], m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr, D.n_vocab,
+                   ep_f32(logits, ld_logits, nullptr, nullptr, 0), st));
+    STB_TRY(bump_pos(pos, st));
+    return STB_OK;
+}
+
 }  // namespace stb
 
 // ---------------------------------------------------------------------------------------------------------
@@ -496,4 +563,17 @@ extern "C" int stb_decoder_forward(stb_model* m, const int32_t* tokens, int B, i
     STB_TRY(check_weights(m, false, true));
     STB_REQUIRE(ws_bytes >= stb_decoder_ws_bytes(m, B, M), "stb_decoder_forward: workspace %zu < %zu", ws_bytes, stb_decoder_ws_bytes(m, B, M));
     return stb::decoder_forward(m, tokens, B, M, cross_kv, logits, ld_logits, qk_out, sel_pairs_host, n_sel, ws, (cudaStream_t)stream);
+}
+
+extern "C" size_t stb_decode_state_bytes(const stb_model* m, int B) { return m ? stb::decode_state_bytes(m, B) : 0; }
+extern "C" size_t stb_decode_ws_bytes(const stb_model* m, int B) { return m ? stb::carve_step(m, B, nullptr).bytes : 0; }
+
+extern "C" int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const void* cross_kv, void* state,
+                               float* logits_out, long long ld_logits, void* ws, size_t ws_bytes, void* stream) {
+    STB_REQUIRE(m && tokens_in && pos && cross_kv && state && logits_out && ws && B >= 1, "stb_decode_step: bad arguments");
+    STB_REQUIRE(ld_logits >= m->dims.n_vocab && ld_logits % 4 == 0, "stb_decode_step: ld_logits must be >= n_vocab and a multiple of 4");
+    STB_REQUIRE(m->dims.n_text_ctx <= 448, "stb_decode_step: n_text_ctx > 448 unsupported");
+    STB_TRY(check_weights(m, false, true));
+    STB_REQUIRE(ws_bytes >= stb_decode_ws_bytes(m, B), "stb_decode_step: workspace too small");
+    return stb::decode_step(m, tokens_in, B, pos, cross_kv, state, logits_out, ld_logits, ws, (cudaStream_t)stream);
 }

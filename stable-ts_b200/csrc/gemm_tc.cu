@@ -443,6 +443,11 @@ int gemm(const stb_operand& A, const stb_operand& B, int n_batch, int n_head, co
     const int passes = A.lo ? 3 : 1;
     const int N = B.rows;
     int BN = N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : 128;
+    if (A.rows <= 128 && n_batch * n_head == 1) {
+        // decode-step shape (M = batch of sequences): HBM-bound on the weights; use narrow N tiles so that enough CTAs
+        // (>= ~120 of the 148 SMs) stream them concurrently
+        while (BN > 16 && cdiv(N, BN) < 120) BN >>= 1;
+    }
     GemmArgs g;
     memset(&g, 0, sizeof(g));
     g.M = A.rows; g.N = N; g.K = A.k; g.H = n_head;

@@ -24,4 +24,12 @@ int im2col3(const __half* src, int B, int C, int Tin_pad, int Tout, int stride, 
 int capture_heads(const float* S, int B, int H, int M, long long ld, float* out, int n_sel, const CaptureList& list,
                   cudaStream_t st);
 
+int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
+                     __half* ol, cudaStream_t st);
+int decode_attn_cross(const float* q, const __half* kh, const __half* kl, const __half* vh, const __half* vl, int B, int H,
+                      int d, __half* oh, __half* ol, cudaStream_t st);
+int embed_step(const int32_t* tokens, const int32_t* pos, int B, int d, const float* emb, const float* posemb, float* x,
+               cudaStream_t st);
+int bump_pos(int32_t* pos, cudaStream_t st);
+
 }  // namespace stb
