@@ -80,6 +80,31 @@ def main():
         mask = torch.zeros(1501, dtype=torch.bool)
         mask[100:400] = True
         res, _ = decode_stable(model, mel, DecodingOptions(language="en", fp16=False, sample_len=24), ts_token_mask=mask)
+        # --- full driver, first window (original_whisper.py:492-710): decode -> segment slicing -> word timestamps
+        import copy
+        import json
+        import stable_whisper.whisper_word_level.original_whisper as ow
+        first = {}
+        orig_awt = ow.add_word_timestamps_stable
+
+        def spy_awt(**kw):
+            orig_awt(**kw)
+            if "segments" not in first:
+                first["segments"] = copy.deepcopy(kw["segments"])
+                first["num_samples"] = int(kw["num_samples"])
+        ow.add_word_timestamps_stable = spy_awt
+        try:
+            ow.transcribe_stable(model, audio, language="en", temperature=0.0, condition_on_previous_text=False,
+                                 word_timestamps=True, vad=False, suppress_silence=False, suppress_ts_tokens=False,
+                                 regroup=False, verbose=None, fp16=False, ignore_compatibility=True, sample_len=40)
+        finally:
+            ow.add_word_timestamps_stable = orig_awt
+        tr = [dict(start=float(sg["start"]), end=float(sg["end"]), tokens=[int(t) for t in sg["tokens"]],
+                   words=[dict(word=w["word"], start=float(w["start"]), end=float(w["end"]),
+                               probability=float(w["probability"]), tokens=[int(t) for t in w["tokens"]]) for w in sg["words"]])
+              for sg in first["segments"]]
+        with open(os.path.join(GOLD, f"{name}_transcribe.json"), "w") as f:
+            json.dump(dict(num_samples=first["num_samples"], segments=tr), f)
         np.savez_compressed(
             os.path.join(GOLD, f"{name}.npz"),
             dims=np.array([getattr(dims, f) for f in dims.__dataclass_fields__], dtype=np.int64),

@@ -52,7 +52,7 @@ def token_row(tokenizer, text_tokens: Sequence[int]) -> List[int]:
     return [*tokenizer.sot_sequence, tokenizer.no_timestamps, *text_tokens, tokenizer.eot]
 
 
-def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, enc=None, heads=None,
+def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, enc=None, ckv=None, heads=None,
                          want_logits: bool = True):
     """Device side of ``_compute_qks`` for a batch of windows.  Returns dict(enc, ckv, logits, qk, M, S, rows)."""
     B = len(jobs)
@@ -64,7 +64,8 @@ def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *
         audio = audio.pin_memory().to(model.device, non_blocking=True)
         mel = model.log_mel(audio)                         # == log_mel_spectrogram(audio, padding=N_SAMPLES-n)
         enc = model.encode(mel)
-    ckv = model.cross_kv(enc)
+    if ckv is None:                                        # cross K/V of the window batch (reused from the decode pass)
+        ckv = model.cross_kv(enc)
     S = len(tokenizer.sot_sequence)
     rows = [token_row(tokenizer, j.text_tokens) for j in jobs]
     M = max(len(r) for r in rows)
@@ -77,12 +78,12 @@ def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *
 
 
 def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfilt_width: int = 7, qk_scale: float = 1.0,
-                  enc=None, return_intermediates: bool = False):
+                  enc=None, ckv=None, return_intermediates: bool = False):
     """Batched equivalent of ``_compute_jump_indices`` (legacy alignment-head path).
 
     -> list (per window) of (jump_indices int array [N+1], text_token_probs list[N]) (+ intermediates).
     """
-    fw = window_batch_forward(model, tokenizer, jobs, enc=enc)
+    fw = window_batch_forward(model, tokenizer, jobs, enc=enc, ckv=ckv)
     S, logits, qk = fw["S"], fw["logits"], fw["qk"]
     out, inter = [], []
     # windows with the same (N, F) share one post-processing / DTW launch
@@ -238,6 +239,72 @@ def merge_punctuations(alignment: List[WordTiming], prepended: str, appended: st
 
 PREPEND_PUNCT = "\"'“¿([{-"
 APPEND_PUNCT = "\"'.。,，!！?？:：”)]}、"
+
+
+def _prepare_word_timestamps(segments, tokenizer, split_callback, gap_padding, pad_first_seg):
+    for seg in segments:
+        seg["words"] = []
+    text_tokens, (words, word_tokens), seg_indices = split_word_tokens(segments, tokenizer, padding=gap_padding,
+                                                                       split_callback=split_callback,
+                                                                       pad_first_seg=pad_first_seg)
+    words = list(words) + [tokenizer.decode([tokenizer.eot])]
+    word_tokens = list(word_tokens) + [[tokenizer.eot]]
+    return text_tokens, words, word_tokens, seg_indices
+
+
+def _finish_word_timestamps(segments, alignment, seg_indices, prepend_punctuations, append_punctuations, min_word_dur,
+                            gap_padding, pad_first_seg):
+    alt_begin = pop_empty_alignment(alignment, seg_indices)
+    merge_punctuations(alignment, prepend_punctuations, append_punctuations)
+    offset = segments[0]["seek"]
+    assert len(alignment) == len(seg_indices)
+    assert gap_padding is None or len(segments) == len(alt_begin) + (1, 0)[pad_first_seg]
+    for i, timing in zip(seg_indices, alignment):
+        if len(timing.tokens) == 0:
+            continue
+        start, end = timing.start, timing.end
+        if len(segments[i]["words"]) == 0 and (end - start) < min_word_dur and i in alt_begin:
+            start = alt_begin[i].start
+        segments[i]["words"].append(dict(word=timing.word, start=round(offset + start, 3), end=round(offset + end, 3),
+                                         probability=timing.probability, tokens=timing.tokens))
+    for seg in segments:
+        if seg["words"]:
+            seg["start"] = seg["words"][0]["start"]
+            seg["end"] = seg["words"][-1]["end"]
+
+
+def add_word_timestamps_batch(windows: List[dict], model: B200Whisper, tokenizer, *, enc=None, ckv=None,
+                              prepend_punctuations: Optional[str] = PREPEND_PUNCT,
+                              append_punctuations: Optional[str] = APPEND_PUNCT, min_word_dur: float = 0.1,
+                              split_callback: Optional[Callable] = None, gap_padding: Optional[str] = " ...",
+                              pad_first_seg: bool = True, medfilt_width: int = 7, qk_scale: float = 1.0):
+    """Batched ``add_word_timestamps_stable``: ``windows`` = list of dict(segments, num_samples[, audio]); all windows
+    share ONE encoder/decoder/DTW batch (``enc`` = the dict from ``model.encode`` for the same windows, in order).
+    Windows without segments are skipped (timing.py:430-431)."""
+    min_word_dur = min_word_dur or 0
+    prepend_punctuations = PREPEND_PUNCT if prepend_punctuations is None else prepend_punctuations
+    append_punctuations = APPEND_PUNCT if append_punctuations is None else append_punctuations
+    live = [i for i, w in enumerate(windows) if len(w["segments"]) > 0]
+    if not live:
+        return
+    prep = {i: _prepare_word_timestamps(windows[i]["segments"], tokenizer, split_callback, gap_padding, pad_first_seg)
+            for i in live}
+    jobs = [WindowJob(list(prep[i][0]), int(windows[i]["num_samples"]), windows[i].get("audio")) for i in live]
+    sub = enc
+    if enc is None or len(live) != enc["B"]:
+        ckv = None                                          # cached cross K/V only matches the full batch
+    if enc is not None and len(live) != enc["B"]:
+        idx = torch.tensor(live, device=model.device)
+        T = L.N_AUDIO_CTX
+        rows = (idx[:, None] * T + torch.arange(T, device=model.device)[None]).reshape(-1)
+        sub = {"f32": enc["f32"].index_select(0, idx), "hi": enc["hi"].index_select(0, rows),
+               "lo": None if enc["lo"] is None else enc["lo"].index_select(0, rows), "B": len(live)}
+    res = align_windows(model, tokenizer, jobs, medfilt_width=medfilt_width, qk_scale=qk_scale, enc=sub, ckv=ckv)
+    for (jumps, probs), i in zip(res, live):
+        _, words, word_tokens, seg_indices = prep[i]
+        alignment = word_timings_from_jumps(jumps, probs, words, word_tokens)
+        _finish_word_timestamps(windows[i]["segments"], alignment, seg_indices, prepend_punctuations, append_punctuations,
+                                min_word_dur, gap_padding, pad_first_seg)
 
 
 def add_word_timestamps_stable(*, segments: List[dict], model: B200Whisper, tokenizer, audio: Optional[torch.Tensor] = None,

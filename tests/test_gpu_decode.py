@@ -96,3 +96,33 @@ def test_forced_script_step_logits_and_argmax():
     assert gx["step_argmax"][:, 0].tolist() == ex["step_argmax"]
     res2, gx2 = decode_windows(gm, tk, enc, DecodingOptions(sample_len=steps), forced_tokens=torch.tensor(script)[:, None])
     assert gx2["step_argmax"][:, 0].tolist() == ex["step_argmax"]          # CUDA-graph replay path
+
+
+@pytest.mark.parametrize("name", ["mini_en", "mini_ml"])
+def test_transcribe_window_matches_reference_driver_fixture(name):
+    """decode -> segment slicing -> gap-padded word timestamps of the first window == what the UNMODIFIED
+    transcribe_stable produced (tests/golden/*_transcribe.json, oracle/make_golden.py)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import json
+    from oracle import stable_path as SP
+    from oracle.whisper_ref.model import ModelDimensions
+    from stable_ts_b200.decode import DecodingOptions
+    from stable_ts_b200.transcribe import transcribe_windows
+    z = np.load(os.path.join(GOLD, f"{name}.npz"))
+    gold = json.load(open(os.path.join(GOLD, f"{name}_transcribe.json")))
+    W, model, gm, tk = _mk(ModelDimensions(*[int(v) for v in z["dims"]]), int(z["model_seed"]))
+    audio = SP.synth_audio(int(z["n_samples"]), seed=1234)
+    segs, info = transcribe_windows(gm, tk, [audio], options=DecodingOptions(language="en", sample_len=40, max_initial_timestamp=None))
+    segs = segs[0]
+    assert [s["tokens"] for s in segs] == [s["tokens"] for s in gold["segments"]]
+    worst = 0.0
+    for s, g in zip(segs, gold["segments"]):
+        assert len(s["words"]) == len(g["words"])
+        assert abs(s["start"] - g["start"]) <= 0.0201 and abs(s["end"] - g["end"]) <= 0.0201
+        for w, gw in zip(s["words"], g["words"]):
+            assert w["tokens"] == gw["tokens"] and w["word"] == gw["word"]
+            worst = max(worst, abs(w["start"] - gw["start"]), abs(w["end"] - gw["end"]))
+            assert abs(w["probability"] - gw["probability"]) <= 2e-3 * gw["probability"] + 1e-12
+    print(f"[{name}] transcribe window: {len(segs)} segments, worst word |dt| {worst:.3f}s")
+    assert worst <= 0.0201
