@@ -40,13 +40,19 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--model", default="large-v3")
+    p.add_argument("--workload", default="transcribe", choices=["transcribe", "align"],
+                   help="transcribe: 224 forced KV-cached decode steps + word timestamps (BASELINE configs 2/4 shape); "
+                        "align: forced alignment of a 100-token script (configs 1/3 shape)")
     p.add_argument("--windows", type=int, default=16, help="30 s windows per GPU per step")
-    p.add_argument("--tokens", type=int, default=100, help="text tokens per window (reference align token_step)")
+    p.add_argument("--tokens", type=int, default=None, help="text tokens per window (default: 224 transcribe / 100 align)")
     p.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     p.add_argument("--cpu-windows", type=int, default=1, help="windows in the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--ncu", action="store_true", help="profiling run: warm up, then ONE step inside cudaProfilerStart/Stop")
-    return p.parse_args()
+    a = p.parse_args()
+    if a.tokens is None:
+        a.tokens = 224 if a.workload == "transcribe" else 100
+    return a
 
 
 # ------------------------------------------------------------------------------------------------- synthetic workload
@@ -167,7 +173,14 @@ def cpu_arm(args, dims_tuple, n_windows, threads=None):
     t0 = time.perf_counter()
     n_words = 0
     for a, wt in zip(audios, wts):
-        n_words += len(SP.align_audio_window(model, tk, wt, a))
+        if args.workload == "align":
+            n_words += len(SP.align_audio_window(model, tk, wt, a))
+        else:                                    # decode.py main loop (forced script) + timing.py alignment pass
+            mel = W.pad_or_trim(W.log_mel_spectrogram(a, model.dims.n_mels), 3000)
+            script = [t for w in wt for t in w]
+            _, af, _ = SP.decode_window(model, mel, forced_tokens=script, sample_len=len(script), language="en",
+                                        max_initial_timestamp=None)
+            n_words += len(SP.align_window(model, tk, wt, mel, len(a), audio_features=af))
     dt = time.perf_counter() - t0
     return n_windows * AUDIO_S / dt, n_words / dt, dt, cores
 
@@ -188,10 +201,10 @@ def run_reference(args, dims_tuple):
     dt = statistics.mean(per_step)
     value = args.cpu_windows * AUDIO_S / dt
     out = {
-        "impl": "reference", "metric": f"rtfx_{args.model}_align", "value": value, "unit": "audio_s/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": f"rtfx_{args.model}_{args.workload}", "value": value, "unit": "audio_s/s", "n_gpus": args.gpus,
         "steps": len(per_step), "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"align {args.model}, {args.cpu_windows} window(s) of 30 s per step, {args.tokens} tokens/window",
+        "config": {"workload": f"{args.workload} {args.model}, {args.cpu_windows} window(s) of 30 s per step, {args.tokens} tokens/window",
                    "weights": "seeded random init"},
         "aligned_words_per_s": words, "rtf": 1.0 / value,
         "cpu_baseline": {"value": value, "unit": "audio_s/s", "cores": cores, "kind": "port",
@@ -230,11 +243,18 @@ def run_b200(args, dims_tuple):
     dev_audio = [h.to(dev) for h in host_audio]
     jobs = [[WindowJob([t for w in wt for t in w], N_SAMPLES, None) for wt in b[1]] for b in batches]
 
+    from stable_ts_b200.decode import DecodingOptions
+    from stable_ts_b200.sharding import run_sharded
+    from stable_ts_b200.transcribe import transcribe_windows
+    scripts = [torch.tensor([[t for w in wt for t in w] for wt in b[1]], dtype=torch.int32).T.contiguous() for b in batches]
+    dopt = DecodingOptions(language="en", sample_len=args.tokens, max_initial_timestamp=None)
+
     def device_step(p):
-        """hot path with inputs resident in HBM; results stay on the device except the tiny jumps/probs read-back"""
-        mel = model.log_mel(dev_audio[p])
-        enc = model.encode(mel)
-        return align_windows(model, tk, jobs[p], enc=enc)
+        """hot path with inputs resident in HBM; only the tiny jumps/probs/token tables are read back"""
+        enc = model.encode(model.log_mel(dev_audio[p]))
+        if args.workload == "align":
+            return align_windows(model, tk, jobs[p], enc=enc)
+        return transcribe_windows(model, tk, None, enc=enc, options=dopt, forced_tokens=scripts[p])
 
     def barrier():
         if world > 1:
@@ -271,16 +291,17 @@ def run_b200(args, dims_tuple):
 
     # ---- e2e: public API with host buffers (+ the one gather of word records when N > 1)
     def e2e_step(p):
-        res = align_words_batch(model, tk, list(host_audio[p]), batches[p][1])
-        rec = torch.tensor([[w["start"], w["end"], w["probability"]] for r in res for w in r], dtype=torch.float32)
-        if world > 1:
-            out = [torch.empty_like(rec, device=dev) for _ in range(world)]
-            dist.all_gather(out, rec.to(dev))
-            rec = torch.cat(out).cpu()
-        return rec
+        def process(lo, hi):                      # this rank's windows (weak scaling: Wn per rank)
+            if args.workload == "align":
+                return align_words_batch(model, tk, list(host_audio[p]), batches[p][1])
+            segs, _ = transcribe_windows(model, tk, list(host_audio[p]), options=dopt, forced_tokens=scripts[p])
+            return [[w for s_ in ws for w in s_["words"]] for ws in segs]
+        return run_sharded(process, world * Wn, device=dev)
 
+    merged = None
     for i in range(max(1, min(args.warmup, 2))):
-        e2e_step(i % pools)
+        merged = e2e_step(i % pools)
+    n_words_total = sum(len(w) for w in merged)          # words actually aligned per step over all ranks
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -329,19 +350,23 @@ def run_b200(args, dims_tuple):
                "sample": f"{args.cpu_windows} window(s) of the same workload ({dt:.1f} s of CPU work), oracle port of the "
                          f"reference CPU path, fp32, torch threads = {cores}"}
     out = {
-        "metric": f"rtfx_{args.model}_align", "value": value, "unit": "audio_s/s", "n_gpus": world, "steps": args.steps,
+        "metric": f"rtfx_{args.model}_{args.workload}", "value": value, "unit": "audio_s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 x3 split (fp32-grade), fp32 accumulate" if args.precision == "fp16x3" else "f16, fp32 accumulate",
         "data": "synthetic",
-        "config": {"workload": f"align {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} text tokens/window "
-                               f"(config 3 shape at the metric's model)",
+        "config": {"workload": (f"transcribe+word_timestamps {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} forced "
+                                "KV-cached decode steps then word alignment (BASELINE configs 2/4 shape)") if args.workload == "transcribe"
+                   else (f"align {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} text tokens/window "
+                         "(BASELINE configs 1/3 shape)"),
                    "weights": "seeded random init at true shapes", "precision": args.precision,
                    "l2": "per-step working set (weights 6.2 GB + activations) >> 126 MB L2; inputs rotate between 2 pools"},
-        "rtf": 1.0 / value, "aligned_words_per_s": world * n_words_step / (ms_step / 1e3),
+        "rtf": 1.0 / value, "aligned_words_per_s": n_words_total / (ms_step / 1e3),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "audio_s/s", "h2d_bytes_per_step": Wn * N_SAMPLES * 4,
-                "d2h_bytes_per_step": int(Wn * (args.tokens + 1) * 4 + Wn * args.tokens * 4), "ms_per_step": e2e_s * 1e3,
-                "aligned_words_per_s": world * n_words_step / e2e_s},
+                # jumps int32 [N+1] + token probs fp32 [N] per window (+ token/argmax tables and sampler state for decode)
+                "d2h_bytes_per_step": int(Wn * ((args.tokens + 3) * 4 + (args.tokens + 2) * 4)
+                                          + (Wn * (2 * args.tokens * 4 + 24 + 4) if args.workload == "transcribe" else 0)),
+                "ms_per_step": e2e_s * 1e3, "aligned_words_per_s": n_words_total / e2e_s},
     }
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -65,18 +65,23 @@ def slice_segments(tokens: Sequence[int], tokenizer, time_offset: float, segment
 def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Tensor], *, time_offsets: Optional[Sequence[float]] = None,
                        word_timestamps: bool = True, options: Optional[DecodingOptions] = None,
                        ts_token_mask: Optional[torch.Tensor] = None, forced_tokens: Optional[torch.Tensor] = None,
-                       gap_padding: Optional[str] = " ...", min_word_dur: float = 0.1, punctuations: str = "\"'“¿([{-\"'.。,，!！?？:：”)]}、"):
-    """B independent <=30 s windows -> list (per window) of segment dicts with ``words``."""
-    B = len(audios)
+                       gap_padding: Optional[str] = " ...", min_word_dur: float = 0.1, punctuations: str = "\"'“¿([{-\"'.。,，!！?？:：”)]}、",
+                       enc: Optional[dict] = None, n_samples: Optional[Sequence[int]] = None):
+    """B independent <=30 s windows -> list (per window) of segment dicts with ``words``.
+    ``enc`` (+ ``n_samples``) may be passed instead of ``audios`` when the encoder output is already on the device."""
+    if enc is None:
+        B = len(audios)
+        batch = torch.zeros(B, N_SAMPLES, dtype=torch.float32)
+        n_samples = []
+        for i, a in enumerate(audios):
+            a = a.detach().float().flatten()[:N_SAMPLES]
+            batch[i, : a.numel()] = a
+            n_samples.append(int(a.numel()))
+        mel = model.log_mel(batch.pin_memory().to(model.device, non_blocking=True))
+        enc = model.encode(mel)
+    B = enc["B"]
+    n_samples = list(n_samples) if n_samples is not None else [N_SAMPLES] * B
     offs = list(time_offsets) if time_offsets is not None else [0.0] * B
-    batch = torch.zeros(B, N_SAMPLES, dtype=torch.float32)
-    n_samples = []
-    for i, a in enumerate(audios):
-        a = a.detach().float().flatten()[:N_SAMPLES]
-        batch[i, : a.numel()] = a
-        n_samples.append(int(a.numel()))
-    mel = model.log_mel(batch.pin_memory().to(model.device, non_blocking=True))
-    enc = model.encode(mel)
     if options is None:                      # transcribe_stable defaults max_initial_timestamp to None (original_whisper.py:262-263)
         options = DecodingOptions(max_initial_timestamp=None)
     results, extras = decode_windows(model, tokenizer, enc, options, ts_token_mask=ts_token_mask,
