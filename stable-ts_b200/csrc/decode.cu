@@ -21,7 +21,8 @@ namespace stb {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, float* __restrict__ Vc, int d, int ctx,
-                        const int32_t* __restrict__ pos_ptr, __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+                        const int32_t* __restrict__ pos_ptr, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                        float* __restrict__ out_f32) {
     __shared__ float s_q[64];
     __shared__ float s_p[448 + 32];
     __shared__ float s_red[4];
@@ -75,94 +76,129 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
     __syncthreads();
     if (tid < 64) {
         const float o = (s_o[0][tid] + s_o[1][tid]) * inv;
-        __half hi, lo;
-        split_f16(o, hi, lo);
-        out_hi[(long long)b * d + h * 64 + tid] = hi;
-        if (out_lo) out_lo[(long long)b * d + h * 64 + tid] = lo;
+        if (out_f32) out_f32[(long long)b * d + h * 64 + tid] = o;
+        if (out_hi) {
+            __half hi, lo;
+            split_f16(o, hi, lo);
+            out_hi[(long long)b * d + h * 64 + tid] = hi;
+            if (out_lo) out_lo[(long long)b * d + h * 64 + tid] = lo;
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // cross-attention over the per-window K (split [B*T][d]) and V^T (split [B][H][64][Tp]).  grid (H, B), 256 threads.
+// HBM-bound (2 x 1500 x 64 x (2+2) B = 768 KB per (sequence, head) per step):
+//   scores: 8 lanes cover one 128-byte key row (hi and lo planes), 4 keys per warp load, 4 loads in flight per lane;
+//   output: warp per head-dim row of V^T, lanes read 8 consecutive keys (16 B) per load, probabilities from smem.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot8(const uint4& a, const float* q) {
+    const __half2* h = reinterpret_cast<const __half2*>(&a);
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        acc = fmaf(q[2 * e], f.x, acc);
+        acc = fmaf(q[2 * e + 1], f.y, acc);
+    }
+    return acc;
+}
+
 __global__ void __launch_bounds__(256)
 decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const __half* __restrict__ k_lo,
                          const __half* __restrict__ v_hi, const __half* __restrict__ v_lo, int d, int T, int Tp,
-                         __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
-    __shared__ float s_q[64];
-    __shared__ float s_p[STB_KPAD];
+                         __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32) {
+    __shared__ __align__(16) float s_p[STB_KPAD + 32];
     __shared__ float s_red[8];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, H = gridDim.x;
-    if (tid < 64) s_q[tid] = q[(long long)b * d + h * 64 + tid];
-    __syncthreads();
+    const int w = tid >> 5, lane = tid & 31;
+    const int sub = lane & 7, grp = lane >> 3;              // 8 lanes per key row, 4 keys per warp load
+    float qr[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e];
+    const long long kbase = (long long)b * T * d + h * 64 + sub * 8;
     float mx = -INFINITY;
-    for (int j = tid; j < T; j += 256) {
-        const long long off = ((long long)b * T + j) * d + h * 64;
-        const uint4* rh = reinterpret_cast<const uint4*>(k_hi + off);
-        const uint4* rl = k_lo ? reinterpret_cast<const uint4*>(k_lo + off) : nullptr;
-        float acc = 0.f;
+    // keys handled by this warp: j = it*32 + w*4 + grp
+    for (int base = 0; base < T; base += 128) {             // warp-uniform trip count (shuffles below); 4 loads in flight
+        const int j0 = base + w * 4 + grp;
+        float part[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const uint4 a = rh[c];
-            const __half2* ah = reinterpret_cast<const __half2*>(&a);
-            float2 f[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) f[e] = __half22float2(ah[e]);
-            if (rl) {
-                const uint4 l = rl[c];
-                const __half2* lh = reinterpret_cast<const __half2*>(&l);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float2 g = __half22float2(lh[e]);
-                    f[e].x += g.x;
-                    f[e].y += g.y;
-                }
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                acc = fmaf(s_q[8 * c + 2 * e], f[e].x, acc);
-                acc = fmaf(s_q[8 * c + 2 * e + 1], f[e].y, acc);
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * 32;
+            part[u] = 0.f;
+            if (j < T) {
+                const long long off = kbase + (long long)j * d;
+                part[u] = dot8(__ldg(reinterpret_cast<const uint4*>(k_hi + off)), qr);
+                if (k_lo) part[u] += dot8(__ldg(reinterpret_cast<const uint4*>(k_lo + off)), qr);
             }
         }
-        acc *= 0.125f;
-        s_p[j] = acc;
-        mx = fmaxf(mx, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v = part[u];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            v += __shfl_xor_sync(0xffffffffu, v, 4);
+            const int j = j0 + u * 32;
+            if (j < T) {
+                v *= 0.125f;
+                if (sub == 0) s_p[j] = v;
+                mx = fmaxf(mx, v);
+            }
+        }
     }
     mx = warp_max(mx);
-    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    if (lane == 0) s_red[w] = mx;
     __syncthreads();
     mx = s_red[0];
 #pragma unroll
     for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
     __syncthreads();
     float sum = 0.f;
-    for (int j = tid; j < T; j += 256) {
-        const float e = expf(s_p[j] - mx);
+    for (int j = tid; j < Tp; j += 256) {
+        const float e = (j < T) ? expf(s_p[j] - mx) : 0.f;   // pad keys get probability 0
         s_p[j] = e;
         sum += e;
     }
     sum = warp_sum(sum);
-    if ((tid & 31) == 0) s_red[tid >> 5] = sum;
+    if (lane == 0) s_red[w] = sum;
     __syncthreads();
     float tot = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) tot += s_red[i];
     const float inv = 1.0f / tot;
-    const int w = tid >> 5, lane = tid & 31;
-    for (int c = w; c < 64; c += 8) {                          // warp per output dim, lanes across keys (coalesced)
+    for (int c = w; c < 64; c += 8) {
         const long long off = (((long long)b * H + h) * 64 + c) * Tp;
+        // Tp = 1504 = 188 x 8: lane l owns 16-byte groups l, l+32, ... (6 trips); all 12 loads are issued before any use
+        uint4 vh[6], vl[6];
+#pragma unroll
+        for (int it = 0; it < 6; ++it) {
+            const int j = (it * 32 + lane) * 8;
+            vh[it] = make_uint4(0, 0, 0, 0);
+            vl[it] = make_uint4(0, 0, 0, 0);
+            if (j < Tp) {
+                vh[it] = __ldg(reinterpret_cast<const uint4*>(v_hi + off + j));
+                if (v_lo) vl[it] = __ldg(reinterpret_cast<const uint4*>(v_lo + off + j));
+            }
+        }
         float acc = 0.f;
-        for (int j = lane; j < T; j += 32) {
-            float v = __half2float(v_hi[off + j]);
-            if (v_lo) v += __half2float(v_lo[off + j]);
-            acc = fmaf(s_p[j], v, acc);
+#pragma unroll
+        for (int it = 0; it < 6; ++it) {
+            const int j = (it * 32 + lane) * 8;
+            if (j < Tp) {                                   // V^T pad columns are zero and p[pad] is zero
+                acc += dot8(vh[it], s_p + j);
+                if (v_lo) acc += dot8(vl[it], s_p + j);
+            }
         }
         acc = warp_sum(acc);
         if (lane == 0) {
-            __half hi, lo;
-            split_f16(acc * inv, hi, lo);
-            out_hi[(long long)b * d + h * 64 + c] = hi;
-            if (out_lo) out_lo[(long long)b * d + h * 64 + c] = lo;
+            const float o = acc * inv;
+            if (out_f32) out_f32[(long long)b * d + h * 64 + c] = o;
+            if (out_hi) {
+                __half hi, lo;
+                split_f16(o, hi, lo);
+                out_hi[(long long)b * d + h * 64 + c] = hi;
+                if (out_lo) out_lo[(long long)b * d + h * 64 + c] = lo;
+            }
         }
     }
 }
@@ -328,14 +364,14 @@ extern "C" int stb_sample_greedy(float* logits, long long ld, int B, int V, int 
 
 namespace stb {
 int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
-                     __half* ol, cudaStream_t st) {
-    decode_self_attn_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, Kc, Vc, d, ctx, pos, oh, ol);
+                     __half* ol, float* of, cudaStream_t st) {
+    decode_self_attn_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, Kc, Vc, d, ctx, pos, oh, ol, of);
     STB_LAUNCH_OK();
     return STB_OK;
 }
 int decode_attn_cross(const float* q, const __half* kh, const __half* kl, const __half* vh, const __half* vl, int B, int H,
-                      int d, __half* oh, __half* ol, cudaStream_t st) {
-    decode_cross_attn_kernel<<<dim3(H, B), 256, 0, st>>>(q, kh, kl, vh, vl, d, STB_N_AUDIO_CTX, STB_KPAD, oh, ol);
+                      int d, __half* oh, __half* ol, float* of, cudaStream_t st) {
+    decode_cross_attn_kernel<<<dim3(H, B), 256, 0, st>>>(q, kh, kl, vh, vl, d, STB_N_AUDIO_CTX, STB_KPAD, oh, ol, of);
     STB_LAUNCH_OK();
     return STB_OK;
 }

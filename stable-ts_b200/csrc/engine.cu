@@ -380,6 +380,8 @@ struct StepWs {
     float* x;
     float* qkv;
     float* q;
+    float* attn_f;     // fp32 activations of the GEMV path (B <= 16)
+    float* hid_f;
     Split ln, attn, hid;
     size_t bytes;
 };
@@ -391,6 +393,8 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.x = c.take<float>((size_t)B * d);
     w.qkv = c.take<float>((size_t)B * 3 * d);
     w.q = c.take<float>((size_t)B * d);
+    w.attn_f = c.take<float>((size_t)B * d);
+    w.hid_f = c.take<float>((size_t)B * 4 * d);
     w.ln = take_split(c, (size_t)B * d, lo);
     w.attn = take_split(c, (size_t)B * d, lo);
     w.hid = take_split(c, (size_t)B * 4 * d, lo);
@@ -409,33 +413,46 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     StepWs w = carve_step(m, B, ws);
     const size_t cache = (size_t)B * ctx * d;
     STB_TRY(embed_step(tokens, pos, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
+    const void* emb_hi = t[STB_T_DEC_TOKEMB][0];
+    const void* emb_lo = m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr;
+    // B <= 16: latency-optimised batched GEMV (mma.sync path, gemv.cu); larger batches: the tcgen05 GEMM core
+    auto lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
+                   const float* res, float* out_f32, Split out_split, long long ld) -> int {
+        if (B <= 16)
+            return gemv(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st);
+        stb_epilogue e;
+        memset(&e, 0, sizeof(e));
+        e.out_f32 = out_f32; e.out_hi = out_split.hi; e.out_lo = out_split.lo; e.ld_out = ld;
+        e.bias = bias; e.act = act; e.residual = res; e.ld_res = ld; e.alpha = 1.0f;
+        return linear(m, x, B, k, w_hi, w_lo, n, e, st);
+    };
+    const Split none = {nullptr, nullptr};
     for (int l = 0; l < D.n_text_layer; ++l) {
         const stb_model::Layer& L = m->dec[l];
         float* Kc = (float*)state + (size_t)l * 2 * cache;
         float* Vc = Kc + cache;
         STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_ATTN_LN_G), W_F32(L, STB_L_ATTN_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
-        STB_TRY(linear(m, w.ln, B, d, W_HI(L, STB_L_QKV_W), W_LO(L, STB_L_QKV_W), 3 * d,
-                       ep_f32(w.qkv, 3 * d, W_F32(L, STB_L_QKV_B), nullptr, 0), st));
-        STB_TRY(decode_attn_self(w.qkv, Kc, Vc, B, H, d, ctx, pos, w.attn.hi, w.attn.lo, st));
-        STB_TRY(linear(m, w.attn, B, d, W_HI(L, STB_L_OUT_W), W_LO(L, STB_L_OUT_W), d,
-                       ep_f32(w.x, d, W_F32(L, STB_L_OUT_B), w.x, d), st));
+        STB_TRY(lin(w.ln, d, W_HI(L, STB_L_QKV_W), W_LO(L, STB_L_QKV_W), 3 * d, W_F32(L, STB_L_QKV_B), STB_ACT_NONE, nullptr,
+                    w.qkv, none, 3 * d));
+        STB_TRY(decode_attn_self(w.qkv, Kc, Vc, B, H, d, ctx, pos, w.attn.hi, w.attn.lo, nullptr, st));
+        STB_TRY(lin(w.attn, d, W_HI(L, STB_L_OUT_W), W_LO(L, STB_L_OUT_W), d, W_F32(L, STB_L_OUT_B), STB_ACT_NONE, w.x, w.x,
+                    none, d));
         STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_CROSS_LN_G), W_F32(L, STB_L_CROSS_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
-        STB_TRY(linear(m, w.ln, B, d, W_HI(L, STB_L_CQ_W), W_LO(L, STB_L_CQ_W), d,
-                       ep_f32(w.q, d, W_F32(L, STB_L_CQ_B), nullptr, 0), st));
+        STB_TRY(lin(w.ln, d, W_HI(L, STB_L_CQ_W), W_LO(L, STB_L_CQ_W), d, W_F32(L, STB_L_CQ_B), STB_ACT_NONE, nullptr, w.q,
+                    none, d));
         Split Kx, vTx;
         cross_ptrs(m, B, ckv, l, Kx, vTx);
-        STB_TRY(decode_attn_cross(w.q, Kx.hi, Kx.lo, vTx.hi, vTx.lo, B, H, d, w.attn.hi, w.attn.lo, st));
-        STB_TRY(linear(m, w.attn, B, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d,
-                       ep_f32(w.x, d, W_F32(L, STB_L_COUT_B), w.x, d), st));
+        STB_TRY(decode_attn_cross(w.q, Kx.hi, Kx.lo, vTx.hi, vTx.lo, B, H, d, w.attn.hi, w.attn.lo, nullptr, st));
+        STB_TRY(lin(w.attn, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d, W_F32(L, STB_L_COUT_B), STB_ACT_NONE, w.x,
+                    w.x, none, d));
         STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
-        STB_TRY(linear(m, w.ln, B, d, W_HI(L, STB_L_FC1_W), W_LO(L, STB_L_FC1_W), 4 * d,
-                       ep_split(w.hid, 4 * d, W_F32(L, STB_L_FC1_B), STB_ACT_GELU), st));
-        STB_TRY(linear(m, w.hid, B, 4 * d, W_HI(L, STB_L_FC2_W), W_LO(L, STB_L_FC2_W), d,
-                       ep_f32(w.x, d, W_F32(L, STB_L_FC2_B), w.x, d), st));
+        STB_TRY(lin(w.ln, d, W_HI(L, STB_L_FC1_W), W_LO(L, STB_L_FC1_W), 4 * d, W_F32(L, STB_L_FC1_B), STB_ACT_GELU, nullptr,
+                    nullptr, w.hid, 4 * d));
+        STB_TRY(lin(w.hid, 4 * d, W_HI(L, STB_L_FC2_W), W_LO(L, STB_L_FC2_W), d, W_F32(L, STB_L_FC2_B), STB_ACT_NONE, w.x, w.x,
+                    none, d));
     }
     STB_TRY(layernorm(w.x, B, d, (const float*)t[STB_T_DEC_LN_G][0], (const float*)t[STB_T_DEC_LN_B][0], w.ln.hi, w.ln.lo, nullptr, st));
-    STB_TRY(linear(m, w.ln, B, d, t[STB_T_DEC_TOKEMB][0], m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr, D.n_vocab,
-                   ep_f32(logits, ld_logits, nullptr, nullptr, 0), st));
+    STB_TRY(lin(w.ln, d, emb_hi, emb_lo, D.n_vocab, nullptr, STB_ACT_NONE, nullptr, logits, none, ld_logits));
     STB_TRY(bump_pos(pos, st));
     return STB_OK;
 }

@@ -25,9 +25,12 @@ int capture_heads(const float* S, int B, int H, int M, long long ld, float* out,
                   cudaStream_t st);
 
 int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
-                     __half* ol, cudaStream_t st);
+                     __half* ol, float* of, cudaStream_t st);
 int decode_attn_cross(const float* q, const __half* kh, const __half* kl, const __half* vh, const __half* vl, int B, int H,
-                      int d, __half* oh, __half* ol, cudaStream_t st);
+                      int d, __half* oh, __half* ol, float* of, cudaStream_t st);
+int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, const void* w_lo, int N, const float* bias,
+         int act, const float* res, long long ld_res, float* out_f32, void* out_hi, void* out_lo, long long ld_out,
+         cudaStream_t st);
 int embed_step(const int32_t* tokens, const int32_t* pos, int B, int d, const float* emb, const float* posemb, float* x,
                cudaStream_t st);
 int bump_pos(int32_t* pos, cudaStream_t st);

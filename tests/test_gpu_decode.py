@@ -126,3 +126,20 @@ def test_transcribe_window_matches_reference_driver_fixture(name):
             assert abs(w["probability"] - gw["probability"]) <= 2e-3 * gw["probability"] + 1e-12
     print(f"[{name}] transcribe window: {len(segs)} segments, worst word |dt| {worst:.3f}s")
     assert worst <= 0.0201
+
+
+def test_decode_large_batch_uses_tensor_core_step_and_matches_gemv_step():
+    """B > 16 takes the tcgen05 small-M path, B <= 16 the batched-GEMV path: same tokens for the same windows."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import stable_path as SP
+    from stable_ts_b200.decode import DecodingOptions, decode_windows
+    W, model, gm, tk = _mk("tiny.en", 8)
+    audios = torch.stack([SP.synth_audio(480000, seed=60 + i) for i in range(3)])
+    big = audios.repeat(6, 1)                                  # 18 windows (3 distinct)
+    opt = DecodingOptions(sample_len=20)
+    r18, _ = decode_windows(gm, tk, gm.encode(gm.log_mel(big.cuda())), opt)
+    r3, _ = decode_windows(gm, tk, gm.encode(gm.log_mel(audios.cuda())), opt)
+    for b in range(18):
+        assert r18[b].tokens == r3[b % 3].tokens
+        assert abs(r18[b].avg_logprob - r3[b % 3].avg_logprob) < 1e-4
