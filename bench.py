@@ -249,12 +249,12 @@ def run_b200(args, dims_tuple):
     scripts = [torch.tensor([[t for w in wt for t in w] for wt in b[1]], dtype=torch.int32).T.contiguous() for b in batches]
     dopt = DecodingOptions(language="en", sample_len=args.tokens, max_initial_timestamp=None)
 
-    def device_step(p):
+    def device_step(p, use_graph=True):
         """hot path with inputs resident in HBM; only the tiny jumps/probs/token tables are read back"""
         enc = model.encode(model.log_mel(dev_audio[p]))
         if args.workload == "align":
             return align_windows(model, tk, jobs[p], enc=enc)
-        return transcribe_windows(model, tk, None, enc=enc, options=dopt, forced_tokens=scripts[p])
+        return transcribe_windows(model, tk, None, enc=enc, options=dopt, forced_tokens=scripts[p], use_graph=use_graph)
 
     def barrier():
         if world > 1:
@@ -316,11 +316,14 @@ def run_b200(args, dims_tuple):
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM core): per-launch CUDA events on the launching stream
     lib.stb_prof_enable(1)
-    device_step(0)
-    import ctypes
-    g_ms, g_fl, g_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
-    L.check(lib.stb_prof_collect(ctypes.byref(g_ms), ctypes.byref(g_fl), ctypes.byref(g_n)))
+    device_step(0, use_graph=False)                    # eager: every launch bracketed by events on its stream
+    prof = L.prof_report()
     lib.stb_prof_enable(0)
+
+    class _V:                                           # keep the field names used below
+        def __init__(self, v): self.value = v
+    gp = prof.get("gemm_tc", {"n": 0, "ms": 0.0, "flops": 0.0})
+    g_ms, g_fl, g_n = _V(gp["ms"]), _V(gp["flops"]), _V(gp["n"])
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -338,6 +341,11 @@ def run_b200(args, dims_tuple):
             "gemm_launches_per_step": int(g_n.value), "gemm_ms_per_step": g_ms.value,
             "gemm_share_of_step": g_ms.value / ms_step if ms_step > 0 else None,
             "algorithmic_gflop_per_window": algorithmic_flops_per_window(model.dims, args.tokens, S) / 1e9}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    kernels = {k: {"launches": v["n"], "ms": round(v["ms"], 3),
+                   "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 and v["bytes"] > 0 else None,
+                   "hbm_frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak, 3) if v["ms"] > 0 and v["bytes"] > 0 else None}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
     if rank != 0:
         if world > 1:
@@ -361,7 +369,7 @@ def run_b200(args, dims_tuple):
                    "weights": "seeded random init at true shapes", "precision": args.precision,
                    "l2": "per-step working set (weights 6.2 GB + activations) >> 126 MB L2; inputs rotate between 2 pools"},
         "rtf": 1.0 / value, "aligned_words_per_s": n_words_total / (ms_step / 1e3),
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "audio_s/s", "h2d_bytes_per_step": Wn * N_SAMPLES * 4,
                 # jumps int32 [N+1] + token probs fp32 [N] per window (+ token/argmax tables and sampler state for decode)
                 "d2h_bytes_per_step": int(Wn * ((args.tokens + 3) * 4 + (args.tokens + 2) * 4)

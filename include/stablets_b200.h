@@ -43,10 +43,12 @@ extern "C" {
 
 STB_API const char* stb_last_error(void);
 STB_API int stb_abi_version(void);
-/* measurement hooks (bench.py): kernels launched by this library so far; per-launch CUDA-event timing of the GEMM core */
+/* measurement hooks (bench.py): kernels launched by this library so far; per-launch CUDA-event timing of every kernel */
 STB_API unsigned long long stb_launch_count(void);
 STB_API void stb_prof_enable(int on);
-STB_API int stb_prof_collect(double* gemm_ms, double* gemm_flops, long long* gemm_launches);
+/* JSON {"kernel": {"n": launches, "ms": event-timed total, "bytes": algorithmic bytes, "flops": algorithmic FLOPs}} of the
+ * launches since the previous report (synchronises the device). */
+STB_API int stb_prof_report(char* buf, size_t buf_bytes);
 
 /* ------------------------------------------------------------------------------------------------------------
  * a1  log-mel front-end.  Replaces whisper.audio.log_mel_spectrogram + pad_or_trim

@@ -44,7 +44,7 @@ _SIGS = {
     "stb_abi_version": (c_int, []),
     "stb_launch_count": (ctypes.c_ulonglong, []),
     "stb_prof_enable": (None, [c_int]),
-    "stb_prof_collect": (c_int, [POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(c_longlong)]),
+    "stb_prof_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "stb_logmel": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                            c_size_t, c_void_p]),
     "stb_gemm": (c_int, [POINTER(Operand), POINTER(Operand), c_int, c_int, POINTER(Epilogue), c_void_p]),
@@ -113,3 +113,11 @@ def ptr(t):
 def stream_ptr():
     import torch
     return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def prof_report() -> dict:
+    """Per-kernel event-timed totals since the last call (see stb_prof_report)."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().stb_prof_report(buf, len(buf)))
+    return json.loads(buf.value.decode())

@@ -52,6 +52,14 @@ const char* get_error();
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Optional per-launch CUDA-event profiling (stb_prof_enable): events are recorded on the launching stream around one
+// kernel; stb_prof_report() aggregates time / algorithmic bytes / algorithmic FLOPs per kernel name.
+struct ProfScope {
+    ProfScope(const char* name, cudaStream_t st, double bytes = 0.0, double flops = 0.0);
+    ~ProfScope();
+    int slot;
+    cudaStream_t st;
+};
 void count_launch();   // every kernel launch of this library bumps the counter read by stb_launch_count()
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 

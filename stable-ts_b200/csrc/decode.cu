@@ -87,8 +87,8 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cross-attention over the per-window K (split [B*T][d]) and V^T (split [B][H][64][Tp]).  grid (H, B), 256 threads.
-// HBM-bound (2 x 1500 x 64 x (2+2) B = 768 KB per (sequence, head) per step):
+// cross-attention over the per-window K (split, head-major [B][H][T][64]) and V^T (split [B][H][64][Tp]).
+// grid (H, B), 256 threads.  HBM-bound (2 x 1500 x 64 x (2+2) B = 768 KB per (sequence, head) per step):
 //   scores: 8 lanes cover one 128-byte key row (hi and lo planes), 4 keys per warp load, 4 loads in flight per lane;
 //   output: warp per head-dim row of V^T, lanes read 8 consecutive keys (16 B) per load, probabilities from smem.
 // ---------------------------------------------------------------------------------------------------------
@@ -116,7 +116,7 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
     float qr[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e];
-    const long long kbase = (long long)b * T * d + h * 64 + sub * 8;
+    const long long kbase = ((long long)b * H + h) * T * 64 + sub * 8;      // K is head-major [B][H][T][64]
     float mx = -INFINITY;
     // keys handled by this warp: j = it*32 + w*4 + grp
     for (int base = 0; base < T; base += 128) {             // warp-uniform trip count (shuffles below); 4 loads in flight
@@ -127,7 +127,7 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
             const int j = j0 + u * 32;
             part[u] = 0.f;
             if (j < T) {
-                const long long off = kbase + (long long)j * d;
+                const long long off = kbase + (long long)j * 64;
                 part[u] = dot8(__ldg(reinterpret_cast<const uint4*>(k_hi + off)), qr);
                 if (k_lo) part[u] += dot8(__ldg(reinterpret_cast<const uint4*>(k_lo + off)), qr);
             }
@@ -354,6 +354,7 @@ extern "C" int stb_sample_greedy(float* logits, long long ld, int B, int V, int 
                                  int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
                                  int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows, void* stream) {
     STB_REQUIRE(logits && states && next_out && B >= 1 && V >= 1 && ld >= V, "stb_sample_greedy: bad arguments");
+    stb::ProfScope ps("sample_greedy", (cudaStream_t)stream, (double)B * V * 4.0 * 3);
     stb::sample_greedy_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(logits, ld, V, eot, ts_begin, no_timestamps, suppress_mask,
                                                                      first_step_mask, ts_mask, max_initial_ts, apply_ts_rules,
                                                                      forced_table, states, next_out, token_table, argmax_table,
@@ -365,12 +366,14 @@ extern "C" int stb_sample_greedy(float* logits, long long ld, int B, int V, int 
 namespace stb {
 int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
                      __half* ol, float* of, cudaStream_t st) {
+    ProfScope ps("decode_self_attn", st);
     decode_self_attn_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, Kc, Vc, d, ctx, pos, oh, ol, of);
     STB_LAUNCH_OK();
     return STB_OK;
 }
 int decode_attn_cross(const float* q, const __half* kh, const __half* kl, const __half* vh, const __half* vl, int B, int H,
                       int d, __half* oh, __half* ol, float* of, cudaStream_t st) {
+    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0 * (kl ? 2 : 1));
     decode_cross_attn_kernel<<<dim3(H, B), 256, 0, st>>>(q, kh, kl, vh, vl, d, STB_N_AUDIO_CTX, STB_KPAD, oh, ol, of);
     STB_LAUNCH_OK();
     return STB_OK;

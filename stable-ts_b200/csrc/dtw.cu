@@ -209,6 +209,7 @@ extern "C" int stb_dtw(const float* x, int B, int R, int F, long long ldx, int n
     }
     STB_REQUIRE(smem <= max_dyn, "stb_dtw: trace needs %zu B of shared memory (limit %zu)", smem, max_dyn);
     const int NW = (R + 31) / 32;
+    stb::ProfScope ps("dtw", (cudaStream_t)stream, (double)B * R * F * 4.0, (double)B * R * F);
     stb::dtw_kernel<<<B, NW * 32, smem, (cudaStream_t)stream>>>(x, R, F, ldx, (long long)R * ldx, negate, jumps, path, path_len);
     STB_LAUNCH_OK();
     return STB_OK;

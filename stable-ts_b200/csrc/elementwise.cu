@@ -64,6 +64,7 @@ int layernorm(const float* x, long long rows, int d, const float* gamma, const f
               float* out_f32, cudaStream_t st) {
     STB_REQUIRE(d % 128 == 0 && d <= 1280, "layernorm: d=%d must be a multiple of 128 and <= 1280", d);
     if (rows == 0) return STB_OK;
+    ProfScope ps("layernorm", st, (double)rows * d * (4.0 + (hi ? 2.0 : 0.0) + (lo ? 2.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
     layernorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, rows, d, gamma, beta, hi, lo, out_f32);
     STB_LAUNCH_OK();
     return STB_OK;
@@ -119,6 +120,7 @@ int softmax_rows(const float* S, long long n_rows, int n_cols, long long ld_s, i
     STB_REQUIRE(n_cols <= SM_MAXV * 32 && ld_p <= SM_MAXV * 32, "softmax: n_cols=%d ld_p=%lld exceed %d", n_cols, ld_p,
                 SM_MAXV * 32);
     if (n_rows == 0) return STB_OK;
+    ProfScope ps("softmax", st, (double)n_rows * n_cols * 4.0 + (double)n_rows * ld_p * 2.0 * (lo ? 2 : 1));
     softmax_kernel<<<cdiv(n_rows, 8), 256, 0, st>>>(S, n_rows, n_cols, ld_s, rows_per_slice, causal, hi, lo, ld_p);
     STB_LAUNCH_OK();
     return STB_OK;
@@ -304,6 +306,7 @@ extern "C" int stb_token_probs(const float* logits, long long ld, int n_rows, in
                                float* prob_out, int32_t* rank_out, void* stream) {
     STB_REQUIRE(logits && targets && prob_out && n_classes > 0 && ld >= n_classes, "stb_token_probs: bad arguments");
     if (n_rows == 0) return STB_OK;
+    stb::ProfScope ps("token_prob", (cudaStream_t)stream, (double)n_rows * n_classes * 4.0);
     stb::token_prob_kernel<<<n_rows, 512, 0, (cudaStream_t)stream>>>(logits, ld, n_classes, targets, prob_out, rank_out);
     STB_LAUNCH_OK();
     return STB_OK;

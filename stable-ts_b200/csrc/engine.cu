@@ -225,7 +225,7 @@ static int encoder_forward(stb_model* m, const float* mel, int B, float* xa_f32,
 // ---------------------------------------------------------------------------------------------------------
 // cross K / V^T for all decoder layers
 // ---------------------------------------------------------------------------------------------------------
-struct CrossKV {             // per layer: K split [B*T][d], vT split [B][H][64][Tp]
+struct CrossKV {             // per layer: K split head-major [B][H][T][64], vT split [B][H][64][Tp]
     size_t k_elems, v_elems, layer_halfs;
 };
 static CrossKV cross_layout(const stb_model* m, int B) {
@@ -252,8 +252,14 @@ static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int 
         const stb_model::Layer& L = m->dec[l];
         Split K, vT;
         cross_ptrs(m, B, out, l, K, vT);
-        STB_TRY(linear(m, xa, (long long)B * T, d, W_HI(L, STB_L_CKV_W), W_LO(L, STB_L_CKV_W), d,
-                       ep_split(K, d, W_F32(L, STB_L_CKV_B), STB_ACT_NONE), st));
+        {   // K head-major [B][H][T][64] (sequential 192 KB streams per (sequence, head) for the decode-step kernel):
+            // per-head batched GEMM, A = xa broadcast over heads, B = rows h*64..h*64+63 of W_k; whisper's key has no bias
+            const int H = D.n_text_head;
+            stb_operand a = opnd(xa.hi, xa.lo, T, d, d, 0, (long long)T * d);
+            stb_operand wk = opnd(W_HI(L, STB_L_CKV_W), W_LO(L, STB_L_CKV_W), 64, d, d, 64LL * d, 0);
+            stb_epilogue e = ep_split(K, 64, nullptr, STB_ACT_NONE, (long long)T * 64, (long long)H * T * 64);
+            STB_TRY(gemm(a, wk, B, H, e, st));
+        }
         STB_TRY(project_vT(m, xa, B, T, d, offs(W_HI(L, STB_L_CKV_W), (long long)d * d), offs(W_LO(L, STB_L_CKV_W), (long long)d * d),
                            W_F32(L, STB_L_CKV_B) + d, vT, STB_KPAD, st));
     }
@@ -325,7 +331,7 @@ static int decoder_forward(stb_model* m, const int32_t* tokens, int B, int M, co
             Split Kx, vTx;
             cross_ptrs(m, B, ckv, l, Kx, vTx);
             stb_operand q = opnd(w.q.hi, w.q.lo, M, 64, d, 64, (long long)M * d);
-            stb_operand k = opnd(Kx.hi, Kx.lo, T, 64, d, 64, (long long)T * d);
+            stb_operand k = opnd(Kx.hi, Kx.lo, T, 64, 64, (long long)T * 64, (long long)H * T * 64);   // head-major K
             stb_epilogue e = ep_f32(w.Sx, Tp, nullptr, nullptr, 0, 0.125f);
             e.out_h_stride = (long long)M * Tp;
             e.out_b_stride = (long long)H * M * Tp;

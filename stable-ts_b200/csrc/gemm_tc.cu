@@ -398,16 +398,6 @@ static int make_tmap(const void* base, int rows, int k, int H, int B, long long 
     return STB_OK;
 }
 
-// ---- optional per-launch CUDA-event profiling (bench.py roofline): events are recorded on the launching stream ----
-struct ProfRec { cudaEvent_t e0, e1; double flops; };
-static bool g_prof_on = false;
-static std::vector<ProfRec> g_prof;
-static std::vector<cudaEvent_t> g_event_pool;
-static cudaEvent_t prof_event() {
-    if (!g_event_pool.empty()) { cudaEvent_t e = g_event_pool.back(); g_event_pool.pop_back(); return e; }
-    cudaEvent_t e; cudaEventCreate(&e); return e;
-}
-
 template <int BN, int PASSES>
 static int launch_gemm(const TmapVal& ah, const TmapVal& al, const TmapVal& bh, const TmapVal& bl, GemmArgs& g,
                        int n_batch, cudaStream_t st) {
@@ -423,14 +413,13 @@ static int launch_gemm(const TmapVal& ah, const TmapVal& al, const TmapVal& bh, 
         g.permB[i] = bh.perm[i];
     }
     dim3 grid(cdiv(g.N, BN), cdiv(g.M, 128), n_batch * g.H);
-    ProfRec rec;
-    if (g_prof_on) {
-        rec.e0 = prof_event(); rec.e1 = prof_event();
-        rec.flops = 2.0 * g.M * (double)g.N * g.K * n_batch * g.H;      // algorithmic (one fp32-grade GEMM), not x PASSES
-        cudaEventRecord(rec.e0, st);
+    {
+        // algorithmic FLOPs of ONE fp32-grade GEMM (not x PASSES); bytes: operands once + output once
+        const double zz = (double)n_batch * g.H;
+        ProfScope ps("gemm_tc", st, zz * ((double)g.M * g.K + (double)g.N * g.K) * 2.0 * Cfg::NPL + zz * (double)g.M * g.N * 4.0,
+                     2.0 * g.M * (double)g.N * g.K * zz);
+        gemm_tc_kernel<BN, PASSES><<<grid, 192, Cfg::SMEM, st>>>(ah.map, al.map, bh.map, bl.map, g);
     }
-    gemm_tc_kernel<BN, PASSES><<<grid, 192, Cfg::SMEM, st>>>(ah.map, al.map, bh.map, bl.map, g);
-    if (g_prof_on) { cudaEventRecord(rec.e1, st); g_prof.push_back(rec); }
     STB_LAUNCH_OK();
     return STB_OK;
 }
@@ -481,24 +470,6 @@ int gemm(const stb_operand& A, const stb_operand& B, int n_batch, int n_head, co
 }
 
 }  // namespace stb
-
-extern "C" void stb_prof_enable(int on) { stb::g_prof_on = on != 0; }
-// Synchronises the device, sums the event-timed GEMM launches recorded since the last collect, then clears them.
-extern "C" int stb_prof_collect(double* gemm_ms, double* gemm_flops, long long* gemm_launches) {
-    STB_CUDA_OK(cudaDeviceSynchronize());
-    double ms = 0, fl = 0;
-    for (auto& r : stb::g_prof) {
-        float t = 0;
-        cudaEventElapsedTime(&t, r.e0, r.e1);
-        ms += t; fl += r.flops;
-        stb::g_event_pool.push_back(r.e0); stb::g_event_pool.push_back(r.e1);
-    }
-    if (gemm_ms) *gemm_ms = ms;
-    if (gemm_flops) *gemm_flops = fl;
-    if (gemm_launches) *gemm_launches = (long long)stb::g_prof.size();
-    stb::g_prof.clear();
-    return STB_OK;
-}
 
 extern "C" int stb_gemm(const stb_operand* A, const stb_operand* B, int n_batch, int n_head, const stb_epilogue* ep,
                         void* stream) {

@@ -4,7 +4,8 @@
 // parity mode), and its enemy is LATENCY, not FLOPs: a 6.5 MB matrix is 1 us of HBM time.  Design:
 //   * one CTA = 8 output features, 8 warps splitting K: at kernel start every lane issues ALL its weight loads
 //     (128-bit, hi and lo planes) -- the whole weight tile of the CTA is in flight after one issue slot;
-//   * meanwhile the 16 x K activation tile (split fp16, L2-resident) is staged into padded shared memory;
+//   * meanwhile the 16 x K activation tile (split fp16, L2-resident) is staged into padded shared memory with
+//     cp.async (all pieces in flight at once, zero-fill for absent rows);
 //   * the products run on the warp-level tensor path, mma.sync m16n8k16 (fp16 x fp16 -> fp32): M = 16 is exactly the
 //     batch, N = 8 the CTA's features.  tcgen05 (M >= 64 atoms, operands via smem descriptors) has no shape for this;
 //     three MMAs per k-step (hi*hi + hi*lo + lo*hi) keep the fp32-grade accuracy of the parity mode;
@@ -67,18 +68,23 @@ gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo
         }
         // ---- 2. stage x[:, kc0:kc0+kc] (16 rows; rows >= B are zero) ----
         if (kc0 > 0) __syncthreads();                        // previous chunk's fragment reads are done
-        const int vec_per_row = kc >> 3;                     // uint4 per row
+        // cp.async (LDGSTS): every 16-byte piece of the tile is in flight at once, no registers, zero-fill for rows >= B
+        const int vec_per_row = kc >> 3;                     // 16-byte pieces per row
         for (int i = threadIdx.x; i < 16 * vec_per_row; i += blockDim.x) {
             const int r = i / vec_per_row, v = i - r * vec_per_row;
-            uint4 h = make_uint4(0, 0, 0, 0), l = make_uint4(0, 0, 0, 0);
-            if (r < B) {
-                const long long off = (long long)r * K + kc0 + v * 8;
-                h = __ldg(reinterpret_cast<const uint4*>(x_hi + off));
-                if (x_lo != nullptr) l = __ldg(reinterpret_cast<const uint4*>(x_lo + off));
-            }
-            *reinterpret_cast<uint4*>(xs_hi + r * pitch + v * 16) = h;
-            *reinterpret_cast<uint4*>(xs_lo + r * pitch + v * 16) = l;
+            const bool ok = r < B;
+            const long long off = (long long)(ok ? r : 0) * K + kc0 + v * 8;
+            const uint32_t dh = smem_u32(xs_hi + r * pitch + v * 16);
+            const uint32_t dl = smem_u32(xs_lo + r * pitch + v * 16);
+            const int nbytes_h = ok ? 16 : 0;
+            const int nbytes_l = (ok && x_lo != nullptr) ? 16 : 0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dh), "l"(x_hi + off), "r"(nbytes_h) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dl), "l"((x_lo != nullptr ? x_lo : x_hi) + off),
+                         "r"(nbytes_l)
+                         : "memory");
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
         // ---- 3. MMAs: k inside a 32-block is permuted so that uint4 {x,y | z,w} are the two k16 steps ----
 #pragma unroll
@@ -143,6 +149,7 @@ int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, con
         STB_CUDA_OK(cudaFuncSetAttribute(gemv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
         configured = want;
     }
+    ProfScope ps("gemv_mma", st, (double)N * K * 2.0 * (w_lo ? 2 : 1) + (double)B * K * 4.0 + (double)B * N * 4.0, 2.0 * B * (double)N * K);
     gemv_mma_kernel<<<cdiv(N, 8), GM_WARPS * 32, smem, st>>>((const __half*)x_hi, (const __half*)x_lo, B, K,
                                                               (const __half*)w_hi, (const __half*)w_lo, N, bias, act, res,
                                                               ld_res, out_f32, (__half*)out_hi, (__half*)out_lo, ld_out);

@@ -1,6 +1,10 @@
 // Error plumbing, device attributes and small utility kernels shared by the C ABI.
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -20,6 +24,26 @@ const char* get_error() { return g_err; }
 static unsigned long long g_launches = 0;
 void count_launch() { ++g_launches; }
 unsigned long long launches() { return g_launches; }
+
+// ---- event profiler ----
+struct ProfRec { const char* name; cudaEvent_t e0, e1; double bytes, flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_events;
+static cudaEvent_t take_event() {
+    if (!g_events.empty()) { cudaEvent_t e = g_events.back(); g_events.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+ProfScope::ProfScope(const char* name, cudaStream_t s, double bytes, double flops) : slot(-1), st(s) {
+    if (!g_prof_on) return;
+    ProfRec r{name, take_event(), take_event(), bytes, flops};
+    cudaEventRecord(r.e0, st);
+    slot = (int)g_prof.size();
+    g_prof.push_back(r);
+}
+ProfScope::~ProfScope() {
+    if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+}
 
 int sm_count() {
     static int n = 0;
@@ -62,5 +86,37 @@ extern "C" int stb_split_f16(const float* src, long long rows, int cols, long lo
     if (blocks > cap) blocks = cap;
     stb::split_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, src_ld, (__half*)hi, (__half*)lo, dst_ld);
     STB_LAUNCH_OK();
+    return STB_OK;
+}
+
+extern "C" void stb_prof_enable(int on) { stb::g_prof_on = on != 0; }
+
+// Synchronises, aggregates the records since the last call per kernel name into `buf` as JSON
+// {"name": {"n": launches, "ms": total, "bytes": algorithmic, "flops": algorithmic}, ...}, then clears them.
+extern "C" int stb_prof_report(char* buf, size_t buf_bytes) {
+    STB_CUDA_OK(cudaDeviceSynchronize());
+    struct Agg { long long n = 0; double ms = 0, bytes = 0, flops = 0; };
+    std::map<std::string, Agg> agg;
+    for (auto& r : stb::g_prof) {
+        float t = 0;
+        cudaEventElapsedTime(&t, r.e0, r.e1);
+        Agg& a = agg[r.name];
+        a.n += 1; a.ms += t; a.bytes += r.bytes; a.flops += r.flops;
+        stb::g_events.push_back(r.e0);
+        stb::g_events.push_back(r.e1);
+    }
+    stb::g_prof.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto& kv : agg) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"n\": %lld, \"ms\": %.6f, \"bytes\": %.0f, \"flops\": %.0f}", first ? "" : ", ",
+                 kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.bytes, kv.second.flops);
+        out += tmp;
+        first = false;
+    }
+    out += "}";
+    STB_REQUIRE(buf && out.size() + 1 <= buf_bytes, "stb_prof_report: buffer too small (%zu needed)", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
     return STB_OK;
 }

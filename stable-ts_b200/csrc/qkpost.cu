@@ -121,6 +121,7 @@ extern "C" int stb_qk_postprocess(const float* qk, int B, int A, int M, long lon
     float* W = (float*)ws;
     cudaStream_t st = (cudaStream_t)stream;
     const long long n_rows = (long long)B * A * R;
+    stb::ProfScope ps("qk_postprocess(3 kernels)", st, (double)B * A * R * F * 4.0 + (double)B * R * F * 4.0);
     stb::qk_softmax_kernel<<<stb::cdiv(n_rows, 8), 256, 0, st>>>(qk, n_rows, M, ldq, S, R, F, qk_scale, W, Fp);
     STB_LAUNCH_OK();
     stb::qk_znorm_kernel<<<dim3(stb::cdiv(F, 128), B * A), 128, 0, st>>>(W, R, F, Fp);

@@ -66,7 +66,7 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                        word_timestamps: bool = True, options: Optional[DecodingOptions] = None,
                        ts_token_mask: Optional[torch.Tensor] = None, forced_tokens: Optional[torch.Tensor] = None,
                        gap_padding: Optional[str] = " ...", min_word_dur: float = 0.1, punctuations: str = "\"'“¿([{-\"'.。,，!！?？:：”)]}、",
-                       enc: Optional[dict] = None, n_samples: Optional[Sequence[int]] = None):
+                       enc: Optional[dict] = None, n_samples: Optional[Sequence[int]] = None, use_graph: bool = True):
     """B independent <=30 s windows -> list (per window) of segment dicts with ``words``.
     ``enc`` (+ ``n_samples``) may be passed instead of ``audios`` when the encoder output is already on the device."""
     if enc is None:
@@ -85,7 +85,7 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
     if options is None:                      # transcribe_stable defaults max_initial_timestamp to None (original_whisper.py:262-263)
         options = DecodingOptions(max_initial_timestamp=None)
     results, extras = decode_windows(model, tokenizer, enc, options, ts_token_mask=ts_token_mask,
-                                     forced_tokens=forced_tokens)
+                                     forced_tokens=forced_tokens, use_graph=use_graph)
     windows = []
     for b in range(B):
         dur = n_samples[b] / SAMPLE_RATE
