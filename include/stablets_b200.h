@@ -101,6 +101,13 @@ typedef struct {
 
 STB_API int stb_gemm(const stb_operand* A, const stb_operand* B, int n_batch, int n_head, const stb_epilogue* ep, void* stream);
 
+/* Fused attention (K4): out[b][m][h*64 + c] = softmax(q k^T / 8) v with scores kept in TMEM (tcgen05) and the
+ * probabilities passed through shared memory.  q: rows Mq, k = 64; k: rows Mk, k = 64; vT: rows 64, k >= Mk (zero padded
+ * keys).  Output split planes with offsets b*out_b_stride + h*out_h_stride + m*ld_out + c.  Non-causal (encoder). */
+STB_API int stb_attention(const stb_operand* q, const stb_operand* k, const stb_operand* vT, int n_batch, int n_head, int Mq,
+                  int Mk, void* out_hi, void* out_lo, long long ld_out, long long out_h_stride, long long out_b_stride,
+                  void* stream);
+
 /* fp32 [rows][cols] (row pitch src_ld) -> split planes (row pitch dst_ld); lo may be NULL */
 STB_API int stb_split_f16(const float* src, long long rows, int cols, long long src_ld, void* hi, void* lo, long long dst_ld,
                   void* stream);

@@ -87,119 +87,168 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cross-attention over the per-window K (split, head-major [B][H][T][64]) and V^T (split [B][H][64][Tp]).
-// grid (H, B), 256 threads.  HBM-bound (2 x 1500 x 64 x (2+2) B = 768 KB per (sequence, head) per step):
-//   scores: 8 lanes cover one 128-byte key row (hi and lo planes), 4 keys per warp load, 4 loads in flight per lane;
-//   output: warp per head-dim row of V^T, lanes read 8 consecutive keys (16 B) per load, probabilities from smem.
+// cross-attention of one new token per sequence over the per-window K and V, both split fp16 and head-major
+// [B][H][T][64]: every (sequence, head) is two contiguous 192 KB streams per plane.  HBM-bound:
+// 2 x 1500 x 64 x (2+2) B = 768 KB per (sequence, head) per step.
+//
+// Flash-decoding layout: the keys of one (b,h) are cut into XS splits; one CTA (4 warps) streams its split ONCE,
+// reading K and V rows of the same key together (8 lanes per 128-byte row, 4 keys per warp load, 16 independent
+// 16-byte loads in flight per lane), with an online softmax per lane group.  Each CTA writes (m, l, acc[64]); the
+// last CTA of a (b,h) to finish (atomic ticket) merges the XS partials and writes the output.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float dot8(const uint4& a, const float* q) {
+constexpr int XS = 4;                       // key splits per (sequence, head)
+constexpr int XS_KEYS = 376;                // keys per split (multiple of 8; 4 x 376 >= 1500)
+
+__device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
     const __half2* h = reinterpret_cast<const __half2*>(&a);
-    float acc = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-        const float2 f = __half22float2(h[e]);
-        acc = fmaf(q[2 * e], f.x, acc);
-        acc = fmaf(q[2 * e + 1], f.y, acc);
+        const float2 t = __half22float2(h[e]);
+        f[2 * e] = t.x;
+        f[2 * e + 1] = t.y;
     }
-    return acc;
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 3)
 decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const __half* __restrict__ k_lo,
-                         const __half* __restrict__ v_hi, const __half* __restrict__ v_lo, int d, int T, int Tp,
-                         __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32) {
-    __shared__ __align__(16) float s_p[STB_KPAD + 32];
-    __shared__ float s_red[8];
-    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, H = gridDim.x;
-    const int w = tid >> 5, lane = tid & 31;
-    const int sub = lane & 7, grp = lane >> 3;              // 8 lanes per key row, 4 keys per warp load
+                         const __half* __restrict__ v_hi, const __half* __restrict__ v_lo, int d, int T,
+                         float* __restrict__ partial, int* __restrict__ tickets, __half* __restrict__ out_hi,
+                         __half* __restrict__ out_lo, float* __restrict__ out_f32) {
+    __shared__ float s_m[4][4], s_l[4][4];
+    __shared__ float s_acc[4][4][64];
+    __shared__ int s_last;
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z, H = gridDim.y;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sub = lane & 7, grp = lane >> 3;
+    const int key0 = split * XS_KEYS, key1 = min(T, key0 + XS_KEYS);
     float qr[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e];
-    const long long kbase = ((long long)b * H + h) * T * 64 + sub * 8;      // K is head-major [B][H][T][64]
-    float mx = -INFINITY;
-    // keys handled by this warp: j = it*32 + w*4 + grp
-    for (int base = 0; base < T; base += 128) {             // warp-uniform trip count (shuffles below); 4 loads in flight
-        const int j0 = base + w * 4 + grp;
-        float part[4];
+    for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e] * 0.125f;
+    const long long base = ((long long)b * H + h) * T * 64 + sub * 8;
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // this lane group's keys: key0 + w*4 + grp + 16*i
+    for (int j0 = key0 + w * 4 + grp; j0 < key1 + 48; j0 += 64) {          // warp-uniform trip count
+        uint4 kh[4], kl[4], vh[4], vl[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u * 32;
-            part[u] = 0.f;
-            if (j < T) {
-                const long long off = kbase + (long long)j * 64;
-                part[u] = dot8(__ldg(reinterpret_cast<const uint4*>(k_hi + off)), qr);
-                if (k_lo) part[u] += dot8(__ldg(reinterpret_cast<const uint4*>(k_lo + off)), qr);
+            const int j = j0 + u * 16;
+            kh[u] = kl[u] = vh[u] = vl[u] = make_uint4(0, 0, 0, 0);
+            if (j < key1) {
+                const long long off = base + (long long)j * 64;
+                kh[u] = __ldg(reinterpret_cast<const uint4*>(k_hi + off));
+                vh[u] = __ldg(reinterpret_cast<const uint4*>(v_hi + off));
+                if (k_lo) {
+                    kl[u] = __ldg(reinterpret_cast<const uint4*>(k_lo + off));
+                    vl[u] = __ldg(reinterpret_cast<const uint4*>(v_lo + off));
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            float v = part[u];
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            const int j = j0 + u * 32;
-            if (j < T) {
-                v *= 0.125f;
-                if (sub == 0) s_p[j] = v;
-                mx = fmaxf(mx, v);
+            const int j = j0 + u * 16;
+            float kf[8], t[8];
+            unpack8(kh[u], kf);
+            if (k_lo) {
+                unpack8(kl[u], t);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) kf[e] += t[e];
+            }
+            float s = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s = fmaf(qr[e], kf[e], s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (j < key1) {                                   // uniform within the 8-lane group
+                const float mn = fmaxf(m, s);
+                const float corr = expf(m - mn);              // exp(-inf) = 0 on the first key
+                const float p = expf(s - mn);
+                float vf[8];
+                unpack8(vh[u], vf);
+                if (v_lo) {
+                    unpack8(vl[u], t);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) vf[e] += t[e];
+                }
+                l = l * corr + p;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e] * corr);
+                m = mn;
             }
         }
     }
-    mx = warp_max(mx);
-    if (lane == 0) s_red[w] = mx;
-    __syncthreads();
-    mx = s_red[0];
+    // ---- combine the 16 lane groups of the CTA ----
+    if (sub == 0) { s_m[w][grp] = m; s_l[w][grp] = l; }
 #pragma unroll
-    for (int i = 1; i < 8; ++i) mx = fmaxf(mx, s_red[i]);
+    for (int e = 0; e < 8; ++e) s_acc[w][grp][sub * 8 + e] = acc[e];
     __syncthreads();
-    float sum = 0.f;
-    for (int j = tid; j < Tp; j += 256) {
-        const float e = (j < T) ? expf(s_p[j] - mx) : 0.f;   // pad keys get probability 0
-        s_p[j] = e;
-        sum += e;
+    float* part = partial + (((long long)b * H + h) * XS + split) * 66;
+    if (threadIdx.x < 64) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) M = fmaxf(M, s_m[i >> 2][i & 3]);
+        float Lsum = 0.f, o = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float mi = s_m[i >> 2][i & 3];
+            const float sc = (mi == -INFINITY) ? 0.f : expf(mi - M);
+            Lsum += s_l[i >> 2][i & 3] * sc;
+            o += s_acc[i >> 2][i & 3][threadIdx.x] * sc;
+        }
+        part[2 + threadIdx.x] = o;
+        if (threadIdx.x == 0) { part[0] = M; part[1] = Lsum; }
     }
-    sum = warp_sum(sum);
-    if (lane == 0) s_red[w] = sum;
+    __threadfence();
     __syncthreads();
-    float tot = 0.f;
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(tickets + b * H + h, 1);
+        s_last = (t == XS - 1);
+        if (s_last) tickets[b * H + h] = 0;                  // re-arm for the next launch
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 64) {
+        __threadfence();
+        const float* p0 = partial + ((long long)b * H + h) * XS * 66;
+        float M = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) tot += s_red[i];
-    const float inv = 1.0f / tot;
-    for (int c = w; c < 64; c += 8) {
-        const long long off = (((long long)b * H + h) * 64 + c) * Tp;
-        // Tp = 1504 = 188 x 8: lane l owns 16-byte groups l, l+32, ... (6 trips); all 12 loads are issued before any use
-        uint4 vh[6], vl[6];
+        for (int i = 0; i < XS; ++i) M = fmaxf(M, __ldcg(p0 + i * 66));
+        float Lsum = 0.f, o = 0.f;
 #pragma unroll
-        for (int it = 0; it < 6; ++it) {
-            const int j = (it * 32 + lane) * 8;
-            vh[it] = make_uint4(0, 0, 0, 0);
-            vl[it] = make_uint4(0, 0, 0, 0);
-            if (j < Tp) {
-                vh[it] = __ldg(reinterpret_cast<const uint4*>(v_hi + off + j));
-                if (v_lo) vl[it] = __ldg(reinterpret_cast<const uint4*>(v_lo + off + j));
-            }
+        for (int i = 0; i < XS; ++i) {
+            const float mi = __ldcg(p0 + i * 66);
+            const float sc = (mi == -INFINITY) ? 0.f : expf(mi - M);
+            Lsum += __ldcg(p0 + i * 66 + 1) * sc;
+            o += __ldcg(p0 + i * 66 + 2 + threadIdx.x) * sc;
         }
-        float acc = 0.f;
-#pragma unroll
-        for (int it = 0; it < 6; ++it) {
-            const int j = (it * 32 + lane) * 8;
-            if (j < Tp) {                                   // V^T pad columns are zero and p[pad] is zero
-                acc += dot8(vh[it], s_p + j);
-                if (v_lo) acc += dot8(vl[it], s_p + j);
-            }
+        o /= Lsum;
+        const long long oo = (long long)b * d + h * 64 + threadIdx.x;
+        if (out_f32) out_f32[oo] = o;
+        if (out_hi) {
+            __half hi, lo;
+            split_f16(o, hi, lo);
+            out_hi[oo] = hi;
+            if (out_lo) out_lo[oo] = lo;
         }
-        acc = warp_sum(acc);
-        if (lane == 0) {
-            const float o = acc * inv;
-            if (out_f32) out_f32[(long long)b * d + h * 64 + c] = o;
-            if (out_hi) {
-                __half hi, lo;
-                split_f16(o, hi, lo);
-                out_hi[(long long)b * d + h * 64 + c] = hi;
-                if (out_lo) out_lo[(long long)b * d + h * 64 + c] = lo;
-            }
-        }
+    }
+}
+
+// V^T split [B][H][64][Tp] -> V split head-major [B][H][T][64] (decode-step layout).  32x32 smem tile transpose.
+__global__ void __launch_bounds__(256) v_headmajor_kernel(const __half* __restrict__ vT, int T, int Tp, __half* __restrict__ v) {
+    __shared__ __half tile[64][72];
+    const long long bh = blockIdx.y;
+    const int t0 = blockIdx.x * 64;
+    const __half* src = vT + bh * 64 * Tp;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int c = i >> 6, t = i & 63;
+        tile[c][t] = (t0 + t < T) ? src[(long long)c * Tp + t0 + t] : __float2half(0.f);
+    }
+    __syncthreads();
+    __half* dst = v + bh * T * 64;
+    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+        const int t = i >> 6, c = i & 63;
+        if (t0 + t < T) dst[(long long)(t0 + t) * 64 + c] = tile[c][t];
     }
 }
 
@@ -372,9 +421,16 @@ int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d
     return STB_OK;
 }
 int decode_attn_cross(const float* q, const __half* kh, const __half* kl, const __half* vh, const __half* vl, int B, int H,
-                      int d, __half* oh, __half* ol, float* of, cudaStream_t st) {
+                      int d, float* partial, int* tickets, __half* oh, __half* ol, float* of, cudaStream_t st) {
     ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0 * (kl ? 2 : 1));
-    decode_cross_attn_kernel<<<dim3(H, B), 256, 0, st>>>(q, kh, kl, vh, vl, d, STB_N_AUDIO_CTX, STB_KPAD, oh, ol, of);
+    decode_cross_attn_kernel<<<dim3(XS, H, B), 128, 0, st>>>(q, kh, kl, vh, vl, d, STB_N_AUDIO_CTX, partial, tickets, oh, ol, of);
+    STB_LAUNCH_OK();
+    return STB_OK;
+}
+size_t decode_cross_scratch_bytes(int B, int H) { return (size_t)B * H * XS * 66 * sizeof(float) + (size_t)B * H * sizeof(int) + 256; }
+int v_headmajor(const __half* vT, int BH, int T, int Tp, __half* v, cudaStream_t st) {
+    ProfScope ps("v_headmajor", st, (double)BH * T * 64 * 4.0);
+    v_headmajor_kernel<<<dim3(cdiv(T, 64), BH), 256, 0, st>>>(vT, T, Tp, v);
     STB_LAUNCH_OK();
     return STB_OK;
 }

@@ -146,8 +146,9 @@ static EncWs carve_encoder(const stb_model* m, int B, void* ws) {
     w.ln = take_split(c, (size_t)B * T * d, lo);
     w.qk = take_split(c, (size_t)B * T * 2 * d, lo);
     w.vT = take_split(c, (size_t)B * d * Tp, lo);
-    w.S = c.take<float>((size_t)B * H * T * Tp);
-    w.P = take_split(c, (size_t)B * H * T * Tp, lo);
+    const bool unfused = getenv("STB_UNFUSED_ATTENTION") != nullptr;   // debugging aid: scores/probabilities through HBM
+    w.S = unfused ? c.take<float>((size_t)B * H * T * Tp) : nullptr;
+    w.P = unfused ? take_split(c, (size_t)B * H * T * Tp, lo) : Split{nullptr, nullptr};
     w.attn = take_split(c, (size_t)B * T * d, lo);
     w.hid = take_split(c, (size_t)B * T * 4 * d, lo);
     w.bytes = c.off;
@@ -207,8 +208,13 @@ static int encoder_forward(stb_model* m, const float* mel, int B, float* xa_f32,
                            W_F32(L, STB_L_QKV_B) + 2 * d, w.vT, Tp, st));
         stb_operand q = opnd(w.qk.hi, w.qk.lo, T, 64, 2 * d, 64, (long long)T * 2 * d);
         stb_operand k = opnd(offs(w.qk.hi, d), offs(w.qk.lo, d), T, 64, 2 * d, 64, (long long)T * 2 * d);
-        AttnBufs ab = {w.S, w.P, w.vT, w.attn};
-        STB_TRY(attention(m, B, H, d, T, T, Tp, q, k, ab, 0, st));
+        if (w.S != nullptr) {
+            AttnBufs ab = {w.S, w.P, w.vT, w.attn};
+            STB_TRY(attention(m, B, H, d, T, T, Tp, q, k, ab, 0, st));
+        } else {                                                   // fused tcgen05 attention: scores never leave the SM
+            stb_operand v = opnd(w.vT.hi, w.vT.lo, 64, Tp, Tp, 64LL * Tp, (long long)d * Tp);
+            STB_TRY(fused_attention(q, k, v, B, H, T, T, w.attn.hi, w.attn.lo, d, 64, (long long)T * d, st));
+        }
         STB_TRY(linear(m, w.attn, rows, d, W_HI(L, STB_L_OUT_W), W_LO(L, STB_L_OUT_W), d,
                        ep_f32(w.x, d, W_F32(L, STB_L_OUT_B), w.x, d), st));
         STB_TRY(layernorm(w.x, rows, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
@@ -225,22 +231,26 @@ static int encoder_forward(stb_model* m, const float* mel, int B, float* xa_f32,
 // ---------------------------------------------------------------------------------------------------------
 // cross K / V^T for all decoder layers
 // ---------------------------------------------------------------------------------------------------------
-struct CrossKV {             // per layer: K split head-major [B][H][T][64], vT split [B][H][64][Tp]
+struct CrossKV {             // per layer: K split head-major [B][H][T][64], vT split [B][H][64][Tp], V split head-major
     size_t k_elems, v_elems, layer_halfs;
 };
 static CrossKV cross_layout(const stb_model* m, int B) {
     CrossKV c;
     c.k_elems = (size_t)B * m->dims.n_audio_ctx * m->dims.n_text_state;
     c.v_elems = (size_t)B * m->dims.n_text_state * STB_KPAD;
-    c.layer_halfs = 2 * (c.k_elems + c.v_elems);             // hi + lo planes of both
+    c.layer_halfs = 2 * (2 * c.k_elems + c.v_elems);         // hi + lo planes of K, V^T and the head-major V copy
     return c;
 }
-static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split& K, Split& vT) {
+static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split& K, Split& vT, Split* Vd = nullptr) {
     CrossKV c = cross_layout(m, B);
     __half* p = (__half*)base + (size_t)l * c.layer_halfs;
     const bool lo = m->prec == STB_PREC_FP16X3;
     K.hi = p; K.lo = lo ? p + c.k_elems : nullptr;
     vT.hi = p + 2 * c.k_elems; vT.lo = lo ? p + 2 * c.k_elems + c.v_elems : nullptr;
+    if (Vd) {
+        __half* v = p + 2 * c.k_elems + 2 * c.v_elems;
+        Vd->hi = v; Vd->lo = lo ? v + c.k_elems : nullptr;
+    }
 }
 
 static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int B, void* out, cudaStream_t st) {
@@ -250,8 +260,8 @@ static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int 
     Split xa = {(__half*)xa_hi, m->prec == STB_PREC_FP16X3 ? (__half*)xa_lo : nullptr};
     for (int l = 0; l < D.n_text_layer; ++l) {
         const stb_model::Layer& L = m->dec[l];
-        Split K, vT;
-        cross_ptrs(m, B, out, l, K, vT);
+        Split K, vT, Vd;
+        cross_ptrs(m, B, out, l, K, vT, &Vd);
         {   // K head-major [B][H][T][64] (sequential 192 KB streams per (sequence, head) for the decode-step kernel):
             // per-head batched GEMM, A = xa broadcast over heads, B = rows h*64..h*64+63 of W_k; whisper's key has no bias
             const int H = D.n_text_head;
@@ -262,6 +272,9 @@ static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int 
         }
         STB_TRY(project_vT(m, xa, B, T, d, offs(W_HI(L, STB_L_CKV_W), (long long)d * d), offs(W_LO(L, STB_L_CKV_W), (long long)d * d),
                            W_F32(L, STB_L_CKV_B) + d, vT, STB_KPAD, st));
+        // head-major copy of V for the decode-step kernel (contiguous per (sequence, head), same layout as K)
+        STB_TRY(v_headmajor(vT.hi, B * D.n_text_head, T, STB_KPAD, Vd.hi, st));
+        if (Vd.lo) STB_TRY(v_headmajor(vT.lo, B * D.n_text_head, T, STB_KPAD, Vd.lo, st));
     }
     return STB_OK;
 }
@@ -386,8 +399,8 @@ struct StepWs {
     float* x;
     float* qkv;
     float* q;
-    float* attn_f;     // fp32 activations of the GEMV path (B <= 16)
-    float* hid_f;
+    float* xpart;      // cross-attention split partials + tickets
+    int* tickets;
     Split ln, attn, hid;
     size_t bytes;
 };
@@ -399,8 +412,8 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.x = c.take<float>((size_t)B * d);
     w.qkv = c.take<float>((size_t)B * 3 * d);
     w.q = c.take<float>((size_t)B * d);
-    w.attn_f = c.take<float>((size_t)B * d);
-    w.hid_f = c.take<float>((size_t)B * 4 * d);
+    w.xpart = c.take<float>((size_t)B * m->dims.n_text_head * 4 * 66);
+    w.tickets = c.take<int>((size_t)B * m->dims.n_text_head);
     w.ln = take_split(c, (size_t)B * d, lo);
     w.attn = take_split(c, (size_t)B * d, lo);
     w.hid = take_split(c, (size_t)B * 4 * d, lo);
@@ -418,6 +431,7 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     const void* const(*t)[2] = m->t;
     StepWs w = carve_step(m, B, ws);
     const size_t cache = (size_t)B * ctx * d;
+    STB_CUDA_OK(cudaMemsetAsync(w.tickets, 0, (size_t)B * H * sizeof(int), st));      // arm the split-merge tickets
     STB_TRY(embed_step(tokens, pos, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
     const void* emb_hi = t[STB_T_DEC_TOKEMB][0];
     const void* emb_lo = m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr;
@@ -446,9 +460,9 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
         STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_CROSS_LN_G), W_F32(L, STB_L_CROSS_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_CQ_W), W_LO(L, STB_L_CQ_W), d, W_F32(L, STB_L_CQ_B), STB_ACT_NONE, nullptr, w.q,
                     none, d));
-        Split Kx, vTx;
-        cross_ptrs(m, B, ckv, l, Kx, vTx);
-        STB_TRY(decode_attn_cross(w.q, Kx.hi, Kx.lo, vTx.hi, vTx.lo, B, H, d, w.attn.hi, w.attn.lo, nullptr, st));
+        Split Kx, vTx, Vd;
+        cross_ptrs(m, B, ckv, l, Kx, vTx, &Vd);
+        STB_TRY(decode_attn_cross(w.q, Kx.hi, Kx.lo, Vd.hi, Vd.lo, B, H, d, w.xpart, w.tickets, w.attn.hi, w.attn.lo, nullptr, st));
         STB_TRY(lin(w.attn, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d, W_F32(L, STB_L_COUT_B), STB_ACT_NONE, w.x,
                     w.x, none, d));
         STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B), w.ln.hi, w.ln.lo, nullptr, st));

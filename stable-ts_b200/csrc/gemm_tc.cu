@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "kernels.h"
 
 namespace stb {
 
@@ -323,18 +324,14 @@ struct TmapKeyHash {
         return (size_t)h;
     }
 };
-struct TmapVal {
-    CUtensorMap map;
-    int perm[3];
-};
 static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey must be a multiple of 8 bytes");
 
 static std::mutex g_tmap_mu;
 static std::unordered_map<TmapKey, TmapVal, TmapKeyHash> g_tmap_cache;
 
 // 4-D fp16 tensor map over one plane: inner dim = k (contiguous), then (row, head, batch) ordered by increasing stride.
-static int make_tmap(const void* base, int rows, int k, int H, int B, long long rs, long long hs, long long bs,
-                     int box_rows, TmapVal* out) {
+int make_tmap(const void* base, int rows, int k, int H, int B, long long rs, long long hs, long long bs, int box_rows,
+              TmapVal* out) {
     TmapKey key;
     memset(&key, 0, sizeof(key));
     key.base = base; key.rows = rows; key.k = k; key.H = H; key.B = B; key.box_rows = box_rows;

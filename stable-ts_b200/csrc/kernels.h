@@ -10,6 +10,17 @@ struct CaptureList {          // passed by value to the capture kernel
     int slot[32];             // destination index inside qk_out's n_sel dimension
 };
 
+// cached 4-D fp16 TMA tensor map over one plane of a K-major operand view (gemm_tc.cu); perm[i] tells which of
+// (row=0, head=1, batch=2, zero=3) feeds TMA coordinate 1+i
+struct TmapVal {
+    CUtensorMap map;
+    int perm[3];
+};
+int make_tmap(const void* base, int rows, int k, int H, int B, long long rs, long long hs, long long bs, int box_rows,
+              TmapVal* out);
+int fused_attention(const stb_operand& q, const stb_operand& k, const stb_operand& vT, int n_batch, int n_head, int Mq, int Mk,
+                    void* out_hi, void* out_lo, long long ld_out, long long out_h, long long out_b, cudaStream_t st);
+
 int gemm(const stb_operand& A, const stb_operand& B, int n_batch, int n_head, const stb_epilogue& ep, cudaStream_t st);
 
 int layernorm(const float* x, long long rows, int d, const float* gamma, const float* beta, __half* hi, __half* lo,
@@ -27,7 +38,9 @@ int capture_heads(const float* S, int B, int H, int M, long long ld, float* out,
 int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
                      __half* ol, float* of, cudaStream_t st);
 int decode_attn_cross(const float* q, const __half* kh, const __half* kl, const __half* vh, const __half* vl, int B, int H,
-                      int d, __half* oh, __half* ol, float* of, cudaStream_t st);
+                      int d, float* partial, int* tickets, __half* oh, __half* ol, float* of, cudaStream_t st);
+size_t decode_cross_scratch_bytes(int B, int H);
+int v_headmajor(const __half* vT, int BH, int T, int Tp, __half* v, cudaStream_t st);
 int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, const void* w_lo, int N, const float* bias,
          int act, const float* res, long long ld_res, float* out_f32, void* out_hi, void* out_lo, long long ld_out,
          cudaStream_t st);

@@ -156,6 +156,39 @@ def test_gemm_overlapping_rows_is_conv(L, stride_mult, C):
     assert err < 3e-6
 
 
+@pytest.mark.parametrize("Bn,H,Mq,Mk,passes", [(1, 2, 128, 128, 3), (2, 3, 300, 300, 3), (1, 2, 1500, 1500, 3),
+                                                (2, 2, 200, 1500, 3), (1, 2, 1500, 1500, 1)])
+def test_fused_attention_vs_fp64(L, Bn, H, Mq, Mk, passes):
+    """tcgen05 fused attention (scores in TMEM, exact two-pass softmax) vs softmax(q k^T / 8) v in fp64."""
+    g = torch.Generator(device="cuda").manual_seed(Mq + Mk + H)
+    d = 64 * H
+    q = torch.randn(Bn, Mq, d, device="cuda", generator=g) * 1.5
+    k = torch.randn(Bn, Mk, d, device="cuda", generator=g) * 1.5
+    v = torch.randn(Bn, Mk, d, device="cuda", generator=g)
+    ldk = (Mk + 7) // 8 * 8
+    vT = torch.zeros(Bn, H, 64, ldk, device="cuda")
+    vT[..., :Mk] = v.view(Bn, Mk, H, 64).permute(0, 2, 3, 1)
+    lo = passes == 3
+    qh, ql = _split(q, lo)
+    kh, kl = _split(k, lo)
+    vh, vl = _split(vT, lo)
+    oq = L.Operand(L.ptr(qh), L.ptr(ql), Mq, 64, d, 64, Mq * d)
+    ok = L.Operand(L.ptr(kh), L.ptr(kl), Mk, 64, d, 64, Mk * d)
+    ov = L.Operand(L.ptr(vh), L.ptr(vl), 64, ldk, ldk, 64 * ldk, d * ldk)
+    out_hi = torch.zeros(Bn, Mq, d, dtype=torch.float16, device="cuda")
+    out_lo = torch.zeros_like(out_hi)
+    L.check(L.lib().stb_attention(ctypes.byref(oq), ctypes.byref(ok), ctypes.byref(ov), Bn, H, Mq, Mk, L.ptr(out_hi),
+                                  L.ptr(out_lo) if lo else None, d, 64, Mq * d, L.stream_ptr()))
+    torch.cuda.synchronize()
+    out = (out_hi.float() + out_lo.float()).double().cpu()
+    qd, kd, vd = [x.double().cpu().view(Bn, -1, H, 64).permute(0, 2, 1, 3) for x in (q, k, v)]
+    ref = (torch.softmax(qd @ kd.transpose(-1, -2) / 8.0, dim=-1) @ vd).permute(0, 2, 1, 3).reshape(Bn, Mq, d)
+    err = ((out - ref).abs().max() / ref.abs().max()).item()
+    print(f"fused attention B{Bn} H{H} {Mq}x{Mk} passes={passes}: rel err {err:.3e}")
+    assert torch.isfinite(out).all()
+    assert err < (1e-5 if passes == 3 else 5e-3)
+
+
 # --------------------------------------------------------------------------------------------------------- DTW
 def _dtw_gpu(L, x, negate=False, want_path=True):
     from stable_ts_b200 import _lib
