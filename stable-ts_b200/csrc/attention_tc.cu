@@ -202,50 +202,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         constexpr float LOG2E = 1.4426950408889634f;
         const float sc = 0.125f * LOG2E;             // scores in log2 units: exp(x) = exp2(x * log2e)
         float m = -INFINITY, l = 0.f;
-        // ---------------- pass 1: row max / sum
+        // ---------------- pass 1: row max only (the sum is accumulated in pass 2 and applied to O in the epilogue:
+        // softmax(s) v == (sum_j exp(s_j - m) v_j) / (sum_j exp(s_j - m)))
         for (int t = 0; t < NT; ++t) {
             const int st = t & 1;
             mbar_wait(&s_full[st], (t >> 1) & 1, 31);
             tc_fence_after();
-            float tm = -INFINITY;
-            float v[64];
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(TM_S0 + st * 128 + lane_off + half * 64 + c * 32, r);
                 tmem_ld_wait();
+                const int kbase = t * AT_BK + half * 64 + c * 32;
+                if (kbase + 32 <= g.Mk) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int key = t * AT_BK + half * 64 + c * 32 + j;
-                    const float x = (key < g.Mk) ? __uint_as_float(r[j]) * sc : -INFINITY;
-                    v[c * 32 + j] = x;
-                    tm = fmaxf(tm, x);
+                    for (int j = 0; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (kbase + j < g.Mk) m = fmaxf(m, __uint_as_float(r[j]));
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[st]);
-            const float mn = fmaxf(m, tm);
-            if (mn > -INFINITY) {
-                float s = 0.f;
-#pragma unroll
-                for (int j = 0; j < 64; ++j) s += exp2f(v[j] - mn);
-                l = l * exp2f(m - mn) + s;
-                m = mn;
-            }
         }
         // combine the two column halves of every row (named barrier over the 256 softmax threads)
         s_xm[half * AT_BQ + row] = m;
-        s_xl[half * AT_BQ + row] = l;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        {
-            const float m2 = s_xm[(half ^ 1) * AT_BQ + row], l2 = s_xl[(half ^ 1) * AT_BQ + row];
-            const float mn = fmaxf(m, m2);
-            l = l * exp2f(m - mn) + l2 * exp2f(m2 - mn);
-            m = mn;
-        }
+        m = fmaxf(m, s_xm[(half ^ 1) * AT_BQ + row]) * sc;         // row max in log2 units
         asm volatile("bar.sync 1, 256;" ::: "memory");           // exchange area is about to be reused as the P tile
-        const float inv_l = 1.0f / l;
         // ---------------- pass 2: probabilities -> shared memory (A operand of P.V)
         uint8_t* p_hi = sm + Cfg::OFF_P + half * Cfg::P_CHUNK;           // this warp's 64-key chunk
         uint8_t* p_lo = p_hi + 2 * Cfg::P_CHUNK;
@@ -267,7 +253,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
                     for (int e = 0; e < 8; ++e) {
                         const int j = j8 * 8 + e;
                         const int key = t * AT_BK + half * 64 + c * 32 + j;
-                        const float p = (key < g.Mk) ? exp2f(__uint_as_float(r[j]) * sc - m) * inv_l : 0.f;
+                        const float p = (key < g.Mk) ? exp2f(fmaf(__uint_as_float(r[j]), sc, -m)) : 0.f;
+                        l += p;
                         split_f16(p, hi8[e], lo8[e]);
                     }
                     // K-major SWIZZLE_128B: row r -> 128 B at r*128; 16-byte chunk index XOR (r & 7)
@@ -288,6 +275,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         // ---------------- epilogue: O (TMEM cols 256..319) -> split fp16 -> attention output
         mbar_wait(&o_full, 0, 34);
         tc_fence_after();
+        s_xl[half * AT_BQ + row] = l;                              // P buffer is idle again: all P.V MMAs have completed
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float inv_l = 1.0f / (l + s_xl[(half ^ 1) * AT_BQ + row]);
         {
             uint32_t r[32];
             tmem_ld_32x32(TM_O + lane_off + half * 32, r);
@@ -297,7 +287,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
                 __align__(16) __half hi[32];
                 __align__(16) __half lo[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) split_f16(__uint_as_float(r[j]), hi[j], lo[j]);
+                for (int j = 0; j < 32; ++j) split_f16(__uint_as_float(r[j]) * inv_l, hi[j], lo[j]);
                 const long long off = (long long)b * g.out_b + (long long)h * g.out_h + (long long)qrow * g.ld_out + half * 32;
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {

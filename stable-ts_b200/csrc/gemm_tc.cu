@@ -10,7 +10,8 @@
 // accumulator, which reproduces an fp32 GEMM to ~1e-6 relative on the fp16 tensor pipe (the reference's CPU/align
 // path is fp32; SURVEY.md section 7 "precision vs the 1e-3 logits gate").  One pass = STB_PREC_FP16.
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (PERSISTENT: one CTA per SM loops over 128 x BN output tiles; 192 threads; the TMEM accumulator is
+// double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1):
 //   warp 0      : TMA producer  (cp.async.bulk.tensor.4d, SWIZZLE_128B tiles, mbarrier complete_tx)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
 //   warps 2..5  : epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / GELU / residual / scale -> global
@@ -26,7 +27,7 @@
 namespace stb {
 
 struct GemmArgs {
-    int M, N, K, H;
+    int M, N, K, H, Z;        // Z = n_batch * H independent (batch, head) problems
     int permA[3], permB[3];   // which of (row=0, head=1, batch=2) feeds TMA coordinate 1,2,3
     float* out_f32;
     __half* out_hi;
@@ -50,7 +51,7 @@ struct GemmCfg {
     static constexpr int STAGES_RAW = (200 * 1024) / STAGE;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr uint32_t SMEM = STAGES * STAGE + 1024;         // + slack for 1024 B alignment
-    static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr uint32_t TMEM_COLS = 2 * (BN < 32 ? 32 : BN);   // double-buffered accumulator
 };
 
 __device__ __forceinline__ void pick_coords(const int (&perm)[3], int row, int h, int b, int& c1, int& c2, int& c3) {
@@ -72,16 +73,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ __align__(8) uint64_t empty_bar[STAGES];
-    __shared__ __align__(8) uint64_t acc_bar;
+    __shared__ __align__(8) uint64_t acc_full[2];             // MMA -> epilogue: accumulator stage complete
+    __shared__ __align__(8) uint64_t acc_empty[2];            // epilogue -> MMA: accumulator stage drained
     __shared__ uint32_t tmem_slot;
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN;
-    const int m0 = blockIdx.y * 128;
-    const int h = blockIdx.z % g.H;
-    const int b = blockIdx.z / g.H;
     const int num_kb = (g.K + 63) >> 6;
+    // persistent tile loop: tile id -> (z, m block, n block), n fastest so concurrently running CTAs share the A tile in L2
+    const int tiles_n = (g.N + BN - 1) / BN;
+    const int tiles_m = (g.M + 127) >> 7;
+    const long long num_tiles = (long long)tiles_n * tiles_m * g.Z;
+    constexpr uint32_t ACC_COLS = BN < 32 ? 32 : BN;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmAh);
@@ -98,11 +101,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
                 mbar_init(&full_bar[s], 1);
                 mbar_init(&empty_bar[s], 1);
             }
-            mbar_init(&acc_bar, 1);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&acc_full[s], 1);
+                mbar_init(&acc_empty[s], 4);                    // one arrival per epilogue warp
+            }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);
+        tmem_alloc(&tmem_slot, Cfg::TMEM_COLS);                 // 2 accumulator stages
         tmem_relinquish();
     }
     tc_fence_before();
@@ -113,23 +119,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
-            int a1, a2, a3, b1, b2, b3;
-            pick_coords(g.permA, m0, h, b, a1, a2, a3);
-            pick_coords(g.permB, n0, h, b, b1, b2, b3);
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-                mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
-                uint8_t* s = tiles + (size_t)stage * Cfg::STAGE;
-                const int k0 = kb * 64;
-                tma_load_4d(s, &tmAh, &full_bar[stage], k0, a1, a2, a3);
-                if (NPL == 2) tma_load_4d(s + Cfg::A_TILE, &tmAl, &full_bar[stage], k0, a1, a2, a3);
-                tma_load_4d(s + NPL * Cfg::A_TILE, &tmBh, &full_bar[stage], k0, b1, b2, b3);
-                if (NPL == 2) tma_load_4d(s + NPL * Cfg::A_TILE + Cfg::B_TILE, &tmBl, &full_bar[stage], k0, b1, b2, b3);
-                if (++stage == STAGES) {
-                    stage = 0;
-                    phase ^= 1;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int nb = (int)(tile % tiles_n);
+                const int mb = (int)((tile / tiles_n) % tiles_m);
+                const int z = (int)(tile / ((long long)tiles_n * tiles_m));
+                int a1, a2, a3, b1, b2, b3;
+                pick_coords(g.permA, mb * 128, z % g.H, z / g.H, a1, a2, a3);
+                pick_coords(g.permB, nb * BN, z % g.H, z / g.H, b1, b2, b3);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE);
+                    uint8_t* s = tiles + (size_t)stage * Cfg::STAGE;
+                    const int k0 = kb * 64;
+                    tma_load_4d(s, &tmAh, &full_bar[stage], k0, a1, a2, a3);
+                    if (NPL == 2) tma_load_4d(s + Cfg::A_TILE, &tmAl, &full_bar[stage], k0, a1, a2, a3);
+                    tma_load_4d(s + NPL * Cfg::A_TILE, &tmBh, &full_bar[stage], k0, b1, b2, b3);
+                    if (NPL == 2) tma_load_4d(s + NPL * Cfg::A_TILE + Cfg::B_TILE, &tmBl, &full_bar[stage], k0, b1, b2, b3);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
                 }
             }
         }
@@ -140,39 +151,54 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             constexpr uint32_t idesc = umma_idesc_f16(128, BN);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t accum = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&full_bar[stage], phase, 2);
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const int as = it & 1;                          // accumulator stage (double-buffered TMEM)
+                mbar_wait(&acc_empty[as], ((it >> 1) & 1) ^ 1, 4);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(tiles + (size_t)stage * Cfg::STAGE);
-                const uint32_t a_hi = sa, a_lo = sa + Cfg::A_TILE;
-                const uint32_t b_hi = sa + NPL * Cfg::A_TILE, b_lo = b_hi + Cfg::B_TILE;
+                const uint32_t tmem_d = tmem_base + as * ACC_COLS;
+                uint32_t accum = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 2);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(tiles + (size_t)stage * Cfg::STAGE);
+                    const uint32_t a_hi = sa, a_lo = sa + Cfg::A_TILE;
+                    const uint32_t b_hi = sa + NPL * Cfg::A_TILE, b_lo = b_hi + Cfg::B_TILE;
 #pragma unroll
-                for (int pass = 0; pass < PASSES; ++pass) {
-                    // pass 0: hi*hi, pass 1: hi*lo, pass 2: lo*hi
-                    const uint32_t pa = (pass == 2) ? a_lo : a_hi;
-                    const uint32_t pb = (pass == 1) ? b_lo : b_hi;
+                    for (int pass = 0; pass < PASSES; ++pass) {
+                        // pass 0: hi*hi, pass 1: hi*lo, pass 2: lo*hi
+                        const uint32_t pa = (pass == 2) ? a_lo : a_hi;
+                        const uint32_t pb = (pass == 1) ? b_lo : b_hi;
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4) {           // 4 x (K = 16 fp16 = 32 B) per 128 B swizzle row
-                        umma_f16(tmem_base, umma_desc_k128(pa + k4 * 32), umma_desc_k128(pb + k4 * 32), idesc, accum);
-                        accum = 1;
+                        for (int k4 = 0; k4 < 4; ++k4) {       // 4 x (K = 16 fp16 = 32 B) per 128 B swizzle row
+                            umma_f16(tmem_d, umma_desc_k128(pa + k4 * 32), umma_desc_k128(pb + k4 * 32), idesc, accum);
+                            accum = 1;
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);            // frees the smem slot once these MMAs retire
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
                     }
                 }
-                umma_commit(&empty_bar[stage]);                // frees the smem slot once these MMAs retire
-                if (++stage == STAGES) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                umma_commit(&acc_full[as]);                     // accumulator complete -> epilogue
             }
-            umma_commit(&acc_bar);                             // accumulator complete -> epilogue
         }
         __syncwarp();
     } else {
         // ------------------------------------------------ epilogue (4 warps; TMEM lane quarter = warp % 4)
         const int q = warp & 3;
+        int it = 0;
+        for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int nbk = (int)(tile % tiles_n);
+        const int mbk = (int)((tile / tiles_n) % tiles_m);
+        const int z = (int)(tile / ((long long)tiles_n * tiles_m));
+        const int n0 = nbk * BN, m0 = mbk * 128, h = z % g.H, b = z / g.H;
+        const int as = it & 1;
+        const uint32_t tmem_acc = tmem_base + as * ACC_COLS;
         const int m = m0 + q * 32 + lane;
         const bool row_ok = m < g.M;
-        mbar_wait(&acc_bar, 0, 3);
+        mbar_wait(&acc_full[as], (it >> 1) & 1, 3);
         tc_fence_after();
         const long long zo = (long long)b * g.out_b + (long long)h * g.out_h;
         const long long zr = (long long)b * g.res_b + (long long)h * g.res_h;
@@ -184,7 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             float v[CW];
             {
                 uint32_t r[CW];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * CW);
+                const uint32_t taddr = tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * CW);
                 if constexpr (CW == 32) tmem_ld_32x32(taddr, r); else tmem_ld_32x16(taddr, r);
                 tmem_ld_wait();
 #pragma unroll
@@ -282,6 +308,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
             }   // row_ok
             __syncwarp();                                      // reconverge before the next .sync.aligned tcgen05.ld
         }
+        tc_fence_before();                                     // this warp's TMEM reads of the stage are complete
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }   // tile loop
     }
     tc_fence_before();
     __syncthreads();
@@ -409,7 +439,9 @@ static int launch_gemm(const TmapVal& ah, const TmapVal& al, const TmapVal& bh, 
         g.permA[i] = ah.perm[i];
         g.permB[i] = bh.perm[i];
     }
-    dim3 grid(cdiv(g.N, BN), cdiv(g.M, 128), n_batch * g.H);
+    g.Z = n_batch * g.H;
+    const long long num_tiles = (long long)cdiv(g.N, BN) * cdiv(g.M, 128) * g.Z;
+    dim3 grid((unsigned)(num_tiles < sm_count() ? num_tiles : sm_count()));     // persistent: one CTA per SM
     {
         // algorithmic FLOPs of ONE fp32-grade GEMM (not x PASSES); bytes: operands once + output once
         const double zz = (double)n_batch * g.H;
