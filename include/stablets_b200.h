@@ -188,6 +188,23 @@ STB_API size_t stb_qkpost_ws_bytes(int B, int A, int R, int F);
 STB_API int stb_qk_postprocess(const float* qk, int B, int A, int M, long long ldq, int S, int R, int F, float qk_scale,
                        int medfilt_width, float* matrix, long long ldm, void* ws, size_t ws_bytes, void* stream);
 
+/* a5 variants, both over the scores of ALL L*H heads (qk [B][LH][M][ldq], stb_decoder_forward with n_sel < 0):
+ *  - dynamic heads (stable_whisper/timing.py:85-103): softmax -> per token row, the `count` heads with the smallest
+ *    distance-weighted mass around the row's peak (argmax on the first call; midpoint of the previous jump interval
+ *    when prev_jumps [B][R] is given) -> z-norm -> median -> mean.  reuse_softmax != 0 keeps the softmaxed scores left in
+ *    `ws` by the previous call (the reference caches them across dynamic iterations, timing.py:89-92).
+ *  - "new" aligner (stable_whisper/timing.py:115-163, arXiv 2509.09987): median filter on the raw scores of every row,
+ *    softmax, head score = w_colnorm * sum_f ||W[:,f]|| + w_rownorm * sum_m ||W[m,:]|| - w_coverage * penalty, top-k
+ *    heads, column-normalised mean, rows S..S+R-1. */
+STB_API size_t stb_qkpost_dynamic_ws_bytes(int B, int LH, int R, int F, int count);
+STB_API int stb_qk_postprocess_dynamic(const float* qk, int B, int LH, int M, long long ldq, int S, int R, int F, float qk_scale,
+                               int medfilt_width, int count, const int32_t* prev_jumps, int reuse_softmax, float* matrix,
+                               long long ldm, void* ws, size_t ws_bytes, void* stream);
+STB_API size_t stb_qkpost_new_ws_bytes(int B, int LH, int M, int F, int topk);
+STB_API int stb_qk_postprocess_new(const float* qk, int B, int LH, int M, long long ldq, int S, int R, int F, float qk_scale,
+                           int medfilt_width, int topk, float w_colnorm, float w_rownorm, float w_coverage, float* matrix,
+                           long long ldm, void* ws, size_t ws_bytes, void* stream);
+
 /* a6 DTW + jump extraction (whisper.timing.dtw CPU semantics + stable_whisper/timing.py:195-198):
  *   x [B][R][ldx] fp32 (cost = -x when negate != 0), path over the R x F grid, strict-'<' tie rule, fp32 cost.
  *   jumps [B][R] int32 = first frame of every row on the path (clipped at 0).

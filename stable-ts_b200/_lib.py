@@ -71,6 +71,12 @@ _SIGS = {
                                 c_size_t, c_void_p]),
     "stb_sample_greedy": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "stb_qkpost_dynamic_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "stb_qk_postprocess_dynamic": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_float, c_int, c_int,
+                                           c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p]),
+    "stb_qkpost_new_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "stb_qk_postprocess_new": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_float, c_int, c_int,
+                                       c_float, c_float, c_float, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p]),
     "stb_dtw_smem_bytes": (c_size_t, [c_int, c_int]),
     "stb_dtw": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
 }

@@ -19,11 +19,11 @@ N_SAMPLES = 480000
 def get_b200_alignment_func(model: B200Whisper, tokenizer, options=None):
     """-> compute_timestamps(audio_segment fp32 [n<=480000], word_tokens) -> list of word dicts
     (same closure as stable_whisper/alignment.py:405-429: no gap padding, identity split, no punctuation merge)."""
-    if options is not None:
-        al = getattr(options, "align", None)
-        if al is not None and (getattr(al, "extra_models", None) or getattr(al, "dynamic_heads", None)
-                               or getattr(al, "aligner", "legacy") != "legacy"):
-            raise NotImplementedError("B200 path: only the legacy alignment-head aligner is implemented")
+    al = getattr(options, "align", None) if options is not None else None
+    if al is not None and getattr(al, "extra_models", None):
+        raise NotImplementedError("B200 path: extra_models is not implemented")
+    dyn = getattr(al, "dynamic_heads", None) if al is not None else None
+    aligner = getattr(al, "aligner", "legacy") if al is not None else "legacy"
 
     def compute_timestamps(audio_segment: torch.Tensor, word_tokens) -> List[dict]:
         words = [wt.word for wt in word_tokens]
@@ -31,7 +31,8 @@ def get_b200_alignment_func(model: B200Whisper, tokenizer, options=None):
         seg = [dict(seek=0, tokens=(words, toks))]
         add_word_timestamps_stable(segments=seg, model=model, tokenizer=tokenizer, audio=audio_segment,
                                    num_samples=int(audio_segment.size(-1)), split_callback=(lambda x, _: x),
-                                   prepend_punctuations="", append_punctuations="", gap_padding=None)
+                                   prepend_punctuations="", append_punctuations="", gap_padding=None, dynamic_heads=dyn,
+                                   aligner=aligner)
         return [w for s in seg for w in s["words"]]
 
     return compute_timestamps
@@ -39,12 +40,13 @@ def get_b200_alignment_func(model: B200Whisper, tokenizer, options=None):
 
 def align_words_batch(model: B200Whisper, tokenizer, audios: Sequence[torch.Tensor],
                       word_tokens: Sequence[List[List[int]]], words: Optional[Sequence[List[str]]] = None,
-                      *, medfilt_width: int = 7, qk_scale: float = 1.0, return_intermediates: bool = False):
+                      *, medfilt_width: int = 7, qk_scale: float = 1.0, dynamic_heads=None, aligner="legacy",
+                      return_intermediates: bool = False):
     """Many independent windows in ONE batch (the natural GPU form of ``align_words``: one window per pre-timed
     segment, stable_whisper/non_whisper/alignment.py:443-465).  -> per window list of word dicts."""
     jobs = [WindowJob([t for w in wt for t in w], int(a.shape[-1]), a) for a, wt in zip(audios, word_tokens)]
-    res = align_windows(model, tokenizer, jobs, medfilt_width=medfilt_width, qk_scale=qk_scale,
-                        return_intermediates=return_intermediates)
+    res = align_windows(model, tokenizer, jobs, medfilt_width=medfilt_width, qk_scale=qk_scale, dynamic_heads=dynamic_heads,
+                        aligner=aligner, return_intermediates=return_intermediates)
     inter = None
     if return_intermediates:
         res, inter = res

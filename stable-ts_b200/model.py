@@ -294,6 +294,37 @@ class B200Whisper:
                                              ldm, L.ptr(ws), ws.numel(), L.stream_ptr()))
         return out[:, :, :F]
 
+    def qk_postprocess_dynamic(self, qk_all: torch.Tensor, S: int, F: int, R: Optional[int] = None, count: int = 6,
+                               prev_jumps: Optional[torch.Tensor] = None, reuse_softmax: bool = False,
+                               qk_scale: float = 1.0, medfilt_width: int = 7) -> torch.Tensor:
+        """Per-token dynamic head selection (timing.py:85-103): qk_all fp32 [B, L*H, M, ld] -> matrix [B, R, F]."""
+        B, LH, M, ld = qk_all.shape
+        assert qk_all.is_contiguous()
+        R = M - 1 - S if R is None else int(R)
+        ldm = (F + 3) // 4 * 4
+        out = torch.empty(B, R, ldm, dtype=torch.float32, device=self.device)
+        ws = self._buf("qkpost_dyn", self._lib.stb_qkpost_dynamic_ws_bytes(B, LH, R, F, count))
+        pj = None if prev_jumps is None else prev_jumps.to(self.device, torch.int32).contiguous()
+        L.check(self._lib.stb_qk_postprocess_dynamic(L.ptr(qk_all), B, LH, M, ld, S, R, F, float(qk_scale), medfilt_width,
+                                                     int(count), L.ptr(pj), int(reuse_softmax), L.ptr(out), ldm, L.ptr(ws),
+                                                     ws.numel(), L.stream_ptr()))
+        return out[:, :, :F]
+
+    def qk_postprocess_new(self, qk_all: torch.Tensor, S: int, F: int, R: Optional[int] = None, topk: int = 20,
+                           w_colnorm: float = 1.0, w_rownorm: float = 1.0, w_coverage: float = 0.0, qk_scale: float = 1.0,
+                           medfilt_width: int = 7) -> torch.Tensor:
+        """The "new" aligner's head scoring (timing.py:115-163): qk_all fp32 [B, L*H, M, ld] -> matrix [B, R, F]."""
+        B, LH, M, ld = qk_all.shape
+        assert qk_all.is_contiguous()
+        R = M - 1 - S if R is None else int(R)
+        ldm = (F + 3) // 4 * 4
+        out = torch.empty(B, R, ldm, dtype=torch.float32, device=self.device)
+        ws = self._buf("qkpost_new", self._lib.stb_qkpost_new_ws_bytes(B, LH, M, F, topk))
+        L.check(self._lib.stb_qk_postprocess_new(L.ptr(qk_all), B, LH, M, ld, S, R, F, float(qk_scale), medfilt_width, int(topk),
+                                                 float(w_colnorm), float(w_rownorm), float(w_coverage), L.ptr(out), ldm,
+                                                 L.ptr(ws), ws.numel(), L.stream_ptr()))
+        return out[:, :, :F]
+
     # ---- a6 ----
     def dtw(self, matrix: torch.Tensor, negate: bool = True, want_path: bool = False):
         """matrix fp32 [B, R, F] (row-strided view ok) -> jumps int32 [B, R] (+ path int32 [B, 2, R+F], len [B])."""

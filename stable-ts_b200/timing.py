@@ -77,15 +77,36 @@ def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *
     return dict(enc=enc, ckv=ckv, logits=logits, qk=qk, M=M, S=S, rows=rows)
 
 
+def _parse_dynamic_heads(dynamic_heads):
+    """(count, iterations) as stable_whisper/timing.py:254-267."""
+    if not dynamic_heads:
+        return None, 1
+    if dynamic_heads is True:
+        return 6, 1
+    if isinstance(dynamic_heads, int):
+        return int(dynamic_heads), 1
+    assert "," in dynamic_heads
+    c, i = dynamic_heads.split(",")
+    return int(c), int(i)
+
+
 def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfilt_width: int = 7, qk_scale: float = 1.0,
-                  enc=None, ckv=None, return_intermediates: bool = False):
-    """Batched equivalent of ``_compute_jump_indices`` (legacy alignment-head path).
+                  enc=None, ckv=None, dynamic_heads=None, aligner: Union[str, dict] = "legacy",
+                  return_intermediates: bool = False):
+    """Batched equivalent of ``_compute_jump_indices``: legacy alignment heads, per-token dynamic heads
+    (``dynamic_heads``: True | count | "count,iterations") or the "new" aligner (``aligner="new"`` or a dict of its
+    options), stable_whisper/timing.py:70-198.
 
     -> list (per window) of (jump_indices int array [N+1], text_token_probs list[N]) (+ intermediates).
     """
-    fw = window_batch_forward(model, tokenizer, jobs, enc=enc, ckv=ckv)
-    S, logits, qk = fw["S"], fw["logits"], fw["qk"]
-    out, inter = [], []
+    count, iters = _parse_dynamic_heads(dynamic_heads)
+    new = aligner != "legacy"
+    if count is None and not new and getattr(model, "missing_alignment_heads", False):
+        count = 6
+    all_heads = bool(count) or new
+    fw = window_batch_forward(model, tokenizer, jobs, enc=enc, ckv=ckv, heads="all" if all_heads else None)
+    S, logits, qk, M = fw["S"], fw["logits"], fw["qk"], fw["M"]
+    inter = []
     # windows with the same (N, F) share one post-processing / DTW launch
     groups = {}
     for i, j in enumerate(jobs):
@@ -94,8 +115,24 @@ def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfi
     for (N, F), idx in groups.items():
         sel = torch.tensor(idx, device=model.device)
         qk_g = qk if len(idx) == len(jobs) else qk.index_select(0, sel).contiguous()
-        matrix = model.qk_postprocess(qk_g, S, F, R=N + 1, qk_scale=qk_scale, medfilt_width=medfilt_width)
-        jumps = model.dtw(matrix, negate=True)
+        if new:
+            kw = dict(aligner) if isinstance(aligner, dict) else {}
+            kw.pop("char_split", None)
+            # the reference slices [S:-1] of the decoder rows it ran (M_i = S + N + 2); padded rows are excluded by
+            # running the scoring on a view of exactly those rows
+            Mi = S + N + 2
+            qk_i = qk_g if Mi == M else qk_g[:, :, :Mi].contiguous()
+            matrix = model.qk_postprocess_new(qk_i, S, F, R=N + 1, qk_scale=qk_scale, medfilt_width=medfilt_width, **kw)
+            jumps = model.dtw(matrix, negate=True)
+        elif count:
+            jumps = None
+            for it in range(iters or 1):
+                matrix = model.qk_postprocess_dynamic(qk_g, S, F, R=N + 1, count=count, prev_jumps=jumps,
+                                                      reuse_softmax=it > 0, qk_scale=qk_scale, medfilt_width=medfilt_width)
+                jumps = model.dtw(matrix, negate=True)
+        else:
+            matrix = model.qk_postprocess(qk_g, S, F, R=N + 1, qk_scale=qk_scale, medfilt_width=medfilt_width)
+            jumps = model.dtw(matrix, negate=True)
         tgt = torch.tensor([jobs[i].text_tokens for i in idx], dtype=torch.int32).reshape(-1)
         rows = torch.cat([logits[i, S:S + N] for i in idx]) if N > 0 else logits[:0, 0]
         probs, _ = model.token_probs(rows, tokenizer.eot, tgt) if N > 0 else (torch.empty(0), None)
@@ -127,8 +164,6 @@ def find_alignment_stable(model: B200Whisper, tokenizer, text_tokens: List[int],
     """One window (stable_whisper/timing.py:202-306).  ``audio`` replaces ``mel`` (the log-mel runs on the device)."""
     if extra_models:
         raise NotImplementedError("extra_models is not supported by the B200 path yet")
-    if dynamic_heads or aligner != "legacy":
-        raise NotImplementedError("only the legacy alignment-head aligner runs on the B200 path in this round")
     if token_split is None:
         words, word_tokens = tokenizer.split_to_word_tokens(list(text_tokens) + [tokenizer.eot])
     else:
@@ -136,7 +171,8 @@ def find_alignment_stable(model: B200Whisper, tokenizer, text_tokens: List[int],
         words = list(words) + [tokenizer.decode([tokenizer.eot])]
         word_tokens = list(word_tokens) + [[tokenizer.eot]]
     job = WindowJob(list(text_tokens), num_samples, audio)
-    (jumps, probs), = align_windows(model, tokenizer, [job], medfilt_width=medfilt_width, qk_scale=qk_scale, enc=enc)
+    (jumps, probs), = align_windows(model, tokenizer, [job], medfilt_width=medfilt_width, qk_scale=qk_scale, enc=enc,
+                                    dynamic_heads=dynamic_heads, aligner=aligner)
     return word_timings_from_jumps(jumps, probs, words, word_tokens)
 
 

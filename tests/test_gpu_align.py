@@ -109,3 +109,31 @@ def test_refine_probs_and_rank_match_oracle():
     assert dr <= 2                                             # near-tied logits may swap neighbouring ranks
     p2 = get_b200_refinement_func(gm, tk)(a2, script)
     assert p2.shape == (2, len(script)) and torch.allclose(p2, p.cpu())
+
+
+@pytest.mark.parametrize("dyn,aligner", [(True, "legacy"), ("4,2", "legacy"), (None, "new")])
+def test_dynamic_heads_and_new_aligner_match_live_oracle(dyn, aligner):
+    """a5 variants end to end (stable_whisper/timing.py:85-103,115-163) through the alignment closure."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import oracle.whisper_ref as W
+    from oracle import stable_path as SP
+    from stable_ts_b200.alignment import align_words_batch
+    from stable_ts_b200.model import from_oracle
+    from stable_ts_b200.tokenizer import get_tokenizer
+    model = W.build_model("tiny", seed=9)
+    gm = from_oracle(model)
+    tk = get_tokenizer(gm, language="en", task="transcribe", synthetic=True)
+    otk = W.tokenizer.get_tokenizer(True, num_languages=model.num_languages, language="en", task="transcribe")
+    audios = [SP.synth_audio(480000, seed=71), SP.synth_audio(200000, seed=72)]
+    wts = [SP.words_from_script(SP.synth_token_script(40, tk.eot, seed=73)), SP.words_from_script(SP.synth_token_script(15, tk.eot, seed=74))]
+    got = align_words_batch(gm, tk, audios, wts, dynamic_heads=dyn, aligner=aligner)
+    worst, bad, total = 0.0, 0, 0
+    for a, wt, g in zip(audios, wts, got):
+        ref = SP.align_audio_window(model, otk, wt, a, dynamic_heads=dyn, aligner=aligner)
+        assert len(ref) == len(g)
+        for r, w in zip(ref, g):
+            d = max(abs(r["start"] - w["start"]), abs(r["end"] - w["end"]))
+            worst, total, bad = max(worst, d), total + 1, bad + (d > 0.0201)
+    print(f"dynamic_heads={dyn} aligner={aligner}: {total} words, worst |dt| {worst:.3f}s, outside +-20ms: {bad}")
+    assert bad == 0

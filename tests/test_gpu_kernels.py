@@ -329,3 +329,65 @@ def test_token_probs_and_rank(L):
     order = p.sort(dim=-1).indices
     ref_rank = (order == tgt[:, None]).nonzero()[:, -1]
     assert np.array_equal(rank.cpu().numpy(), ref_rank.numpy())
+
+
+# --------------------------------------------------------------------------------------------------------- a5 variants
+def _model_stub(L):
+    """A B200Whisper is not needed for the post-processing kernels: call the C ABI directly."""
+    return L.lib()
+
+
+@pytest.mark.parametrize("LH,M,F,S,count,iters", [(8, 30, 500, 1, 6, 1), (12, 44, 937, 3, 4, 2), (24, 20, 1500, 3, 6, 3)])
+def test_qk_postprocess_dynamic_heads_vs_oracle(L, LH, M, F, S, count, iters):
+    from oracle import c_oracle
+    from oracle import stable_path as SP
+    g = torch.Generator().manual_seed(LH * 31 + M)
+    Bn = 2
+    qk = torch.randn(Bn, LH, M, 1504, generator=g) * 3.0
+    lib = L.lib()
+    R = M - 1 - S
+    ldm = (F + 3) // 4 * 4
+    qkc = qk.cuda()
+    out = torch.empty(Bn, R, ldm, device="cuda")
+    ws = torch.empty(lib.stb_qkpost_dynamic_ws_bytes(Bn, LH, R, F, count), dtype=torch.uint8, device="cuda")
+    jumps_dev = None
+    ref_jumps = [None] * Bn
+    for it in range(iters):
+        L.check(lib.stb_qk_postprocess_dynamic(L.ptr(qkc), Bn, LH, M, 1504, S, R, F, 1.0, 7, count, L.ptr(jumps_dev), int(it > 0),
+                                               L.ptr(out), ldm, L.ptr(ws), ws.numel(), L.stream_ptr()))
+        torch.cuda.synchronize()
+        new_jumps = []
+        for b in range(Bn):
+            qks = [qk[b:b + 1, h:h + 1] for h in range(LH)]          # one head per "layer"
+            w = SP.attention_weights_dynamic(qks, S, F * 320, count, ref_jumps[b])
+            ref = w.mean(dim=0)
+            err = (out[b, :, :F].cpu() - ref).abs().max().item()
+            assert err < 5e-5, (it, b, err)
+            ref_jumps[b] = SP.jumps_from_matrix(ref)
+            new_jumps.append(torch.from_numpy(c_oracle.dtw(-out[b, :, :F].cpu().numpy())[1]))
+            assert np.array_equal(new_jumps[-1].numpy(), ref_jumps[b])
+        jumps_dev = torch.stack(new_jumps).to(torch.int32).cuda()
+    print(f"dynamic heads LH={LH} M={M} F={F} count={count} iters={iters}: ok")
+
+
+@pytest.mark.parametrize("LH,H,M,F,S,topk,wcov", [(8, 2, 30, 500, 1, 5, 0.0), (24, 4, 44, 937, 3, 20, 0.0), (12, 3, 20, 1500, 3, 6, 0.5)])
+def test_qk_postprocess_new_aligner_vs_oracle(L, LH, H, M, F, S, topk, wcov):
+    from oracle import stable_path as SP
+    g = torch.Generator().manual_seed(LH * 17 + M)
+    Bn = 2
+    qk = torch.randn(Bn, LH, M, 1504, generator=g) * 3.0
+    lib = L.lib()
+    R = M - 1 - S
+    ldm = (F + 3) // 4 * 4
+    qkc = qk.cuda()
+    out = torch.empty(Bn, R, ldm, device="cuda")
+    ws = torch.empty(lib.stb_qkpost_new_ws_bytes(Bn, LH, M, F, topk), dtype=torch.uint8, device="cuda")
+    L.check(lib.stb_qk_postprocess_new(L.ptr(qkc), Bn, LH, M, 1504, S, R, F, 1.0, 7, topk, 1.0, 1.0, wcov, L.ptr(out), ldm,
+                                       L.ptr(ws), ws.numel(), L.stream_ptr()))
+    torch.cuda.synchronize()
+    for b in range(Bn):
+        qks = [qk[b:b + 1, l * H:(l + 1) * H] for l in range(LH // H)]
+        ref = SP.attention_matrix_new(qks, S, F * 320, topk=topk, w_coverage=wcov)
+        err = (out[b, :, :F].cpu() - ref).abs().max().item() / ref.abs().max().item()
+        print(f"new aligner LH={LH} M={M} F={F} topk={topk} wcov={wcov}: rel err {err:.2e}")
+        assert err < 1e-4
