@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/stablets_b200.h"
 
@@ -64,6 +65,32 @@ void count_launch();   // every kernel launch of this library bumps the counter 
 int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 
 #ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): a kernel launched with `launch_pdl` may start while its predecessor in the
+// stream is still running; it must execute pdl_wait() before touching anything the predecessor writes.  pdl_trigger()
+// lets the NEXT kernel start early.  Both are no-ops for ordinary launches.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // STB_PDL=0 disables (misc.cu)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // warp helpers
 // ---------------------------------------------------------------------------------------------------------

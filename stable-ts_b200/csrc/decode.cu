@@ -28,6 +28,8 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
     __shared__ float s_red[4];
     __shared__ float s_o[2][64];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const int pos = *pos_ptr;
     const int n = pos + 1;
     const float* row = qkv + (long long)b * 3 * d;
@@ -121,6 +123,8 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int sub = lane & 7, grp = lane >> 3;
     const int key0 = split * XS_KEYS, key1 = min(T, key0 + XS_KEYS);
+    pdl_trigger();
+    pdl_wait();                                              // q comes from the preceding GEMV
     float qr[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e] * 0.125f;
@@ -255,6 +259,8 @@ __global__ void __launch_bounds__(256) v_headmajor_kernel(const __half* __restri
 __global__ void embed_step_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ pos_ptr, int d,
                                   const float* __restrict__ emb, const float* __restrict__ posemb, float* __restrict__ x) {
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const int pos = *pos_ptr;
     const float4* e = reinterpret_cast<const float4*>(emb + (long long)tokens[b] * d);
     const float4* p = reinterpret_cast<const float4*>(posemb + (long long)pos * d);
@@ -302,6 +308,8 @@ sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, i
     __shared__ BlockRed red;
     __shared__ int s_arg;
     const int b = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     float* l = logits + (long long)b * ld;
     stb_seq_state st = states[b];
     const bool first = st.n_sampled == 0;
@@ -394,7 +402,11 @@ sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, i
     }
 }
 
-__global__ void bump_pos_kernel(int32_t* pos) { *pos += 1; }
+__global__ void bump_pos_kernel(int32_t* pos) {
+    pdl_trigger();
+    pdl_wait();
+    *pos += 1;
+}
 
 }  // namespace stb
 
@@ -404,10 +416,9 @@ extern "C" int stb_sample_greedy(float* logits, long long ld, int B, int V, int 
                                  int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows, void* stream) {
     STB_REQUIRE(logits && states && next_out && B >= 1 && V >= 1 && ld >= V, "stb_sample_greedy: bad arguments");
     stb::ProfScope ps("sample_greedy", (cudaStream_t)stream, (double)B * V * 4.0 * 3);
-    stb::sample_greedy_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(logits, ld, V, eot, ts_begin, no_timestamps, suppress_mask,
-                                                                     first_step_mask, ts_mask, max_initial_ts, apply_ts_rules,
-                                                                     forced_table, states, next_out, token_table, argmax_table,
-                                                                     table_rows);
+    STB_CUDA_OK(stb::launch_pdl(stb::sample_greedy_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, logits, ld, V, eot, ts_begin,
+                                no_timestamps, suppress_mask, first_step_mask, ts_mask, max_initial_ts, apply_ts_rules, forced_table,
+                                states, next_out, token_table, argmax_table, table_rows));
     STB_LAUNCH_OK();
     return STB_OK;
 }
@@ -416,14 +427,15 @@ namespace stb {
 int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
                      __half* ol, float* of, cudaStream_t st) {
     ProfScope ps("decode_self_attn", st);
-    decode_self_attn_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, Kc, Vc, d, ctx, pos, oh, ol, of);
+    STB_CUDA_OK(launch_pdl(decode_self_attn_kernel, dim3(H, B), dim3(128), 0, st, qkv, Kc, Vc, d, ctx, pos, oh, ol, of));
     STB_LAUNCH_OK();
     return STB_OK;
 }
 int decode_attn_cross(const float* q, const __half* kh, const __half* kl, const __half* vh, const __half* vl, int B, int H,
                       int d, float* partial, int* tickets, __half* oh, __half* ol, float* of, cudaStream_t st) {
     ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0 * (kl ? 2 : 1));
-    decode_cross_attn_kernel<<<dim3(XS, H, B), 128, 0, st>>>(q, kh, kl, vh, vl, d, STB_N_AUDIO_CTX, partial, tickets, oh, ol, of);
+    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel, dim3(XS, H, B), dim3(128), 0, st, q, kh, kl, vh, vl, d, (int)STB_N_AUDIO_CTX,
+                           partial, tickets, oh, ol, of));
     STB_LAUNCH_OK();
     return STB_OK;
 }
@@ -436,12 +448,12 @@ int v_headmajor(const __half* vT, int BH, int T, int Tp, __half* v, cudaStream_t
 }
 int embed_step(const int32_t* tokens, const int32_t* pos, int B, int d, const float* emb, const float* posemb, float* x,
                cudaStream_t st) {
-    embed_step_kernel<<<B, 128, 0, st>>>(tokens, pos, d, emb, posemb, x);
+    STB_CUDA_OK(launch_pdl(embed_step_kernel, dim3(B), dim3(128), 0, st, tokens, pos, d, emb, posemb, x));
     STB_LAUNCH_OK();
     return STB_OK;
 }
 int bump_pos(int32_t* pos, cudaStream_t st) {
-    bump_pos_kernel<<<1, 1, 0, st>>>(pos);
+    STB_CUDA_OK(launch_pdl(bump_pos_kernel, dim3(1), dim3(1), 0, st, pos));
     STB_LAUNCH_OK();
     return STB_OK;
 }

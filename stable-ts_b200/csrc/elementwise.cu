@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         __half* __restrict__ hi, __half* __restrict__ lo,
                                                         float* __restrict__ out_f32) {
+    pdl_trigger();
+    pdl_wait();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -65,7 +67,7 @@ int layernorm(const float* x, long long rows, int d, const float* gamma, const f
     STB_REQUIRE(d % 128 == 0 && d <= 1280, "layernorm: d=%d must be a multiple of 128 and <= 1280", d);
     if (rows == 0) return STB_OK;
     ProfScope ps("layernorm", st, (double)rows * d * (4.0 + (hi ? 2.0 : 0.0) + (lo ? 2.0 : 0.0) + (out_f32 ? 4.0 : 0.0)));
-    layernorm_kernel<<<cdiv(rows, 8), 256, 0, st>>>(x, rows, d, gamma, beta, hi, lo, out_f32);
+    STB_CUDA_OK(launch_pdl(layernorm_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, st, x, rows, d, gamma, beta, hi, lo, out_f32));
     STB_LAUNCH_OK();
     return STB_OK;
 }

@@ -431,7 +431,6 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     const void* const(*t)[2] = m->t;
     StepWs w = carve_step(m, B, ws);
     const size_t cache = (size_t)B * ctx * d;
-    STB_CUDA_OK(cudaMemsetAsync(w.tickets, 0, (size_t)B * H * sizeof(int), st));      // arm the split-merge tickets
     STB_TRY(embed_step(tokens, pos, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
     const void* emb_hi = t[STB_T_DEC_TOKEMB][0];
     const void* emb_lo = m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr;

@@ -49,6 +49,7 @@ gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo
     const bool n_ok = n < N;
     const bool has_lo = w_lo != nullptr;
     float c[4] = {0.f, 0.f, 0.f, 0.f};
+    pdl_trigger();                                           // the next kernel may start its own weight prefetch
 
     for (int kc0 = 0; kc0 < K; kc0 += GM_KC) {
         const int kc = min(GM_KC, K - kc0);
@@ -67,6 +68,7 @@ gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo
             }
         }
         // ---- 2. stage x[:, kc0:kc0+kc] (16 rows; rows >= B are zero) ----
+        if (kc0 == 0) pdl_wait();                            // weights are constants; x / res / out belong to predecessors
         if (kc0 > 0) __syncthreads();                        // previous chunk's fragment reads are done
         // cp.async (LDGSTS): every 16-byte piece of the tile is in flight at once, no registers, zero-fill for rows >= B
         const int vec_per_row = kc >> 3;                     // 16-byte pieces per row
@@ -150,9 +152,9 @@ int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, con
         configured = want;
     }
     ProfScope ps("gemv_mma", st, (double)N * K * 2.0 * (w_lo ? 2 : 1) + (double)B * K * 4.0 + (double)B * N * 4.0, 2.0 * B * (double)N * K);
-    gemv_mma_kernel<<<cdiv(N, 8), GM_WARPS * 32, smem, st>>>((const __half*)x_hi, (const __half*)x_lo, B, K,
-                                                              (const __half*)w_hi, (const __half*)w_lo, N, bias, act, res,
-                                                              ld_res, out_f32, (__half*)out_hi, (__half*)out_lo, ld_out);
+    STB_CUDA_OK(launch_pdl(gemv_mma_kernel, dim3(cdiv(N, 8)), dim3(GM_WARPS * 32), smem, st, (const __half*)x_hi,
+                           (const __half*)x_lo, B, K, (const __half*)w_hi, (const __half*)w_lo, N, bias, act, res, ld_res,
+                           out_f32, (__half*)out_hi, (__half*)out_lo, ld_out));
     STB_LAUNCH_OK();
     return STB_OK;
 }

@@ -1,6 +1,7 @@
 // Error plumbing, device attributes and small utility kernels shared by the C ABI.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <string>
@@ -43,6 +44,15 @@ ProfScope::ProfScope(const char* name, cudaStream_t s, double bytes, double flop
 }
 ProfScope::~ProfScope() {
     if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
+}
+
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("STB_PDL");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
 }
 
 int sm_count() {

@@ -73,7 +73,7 @@ class StepEngine:
         dev, lib, V = model.device, model._lib, model.dims.n_vocab
         self.ldv = (V + 7) // 8 * 8
         self.state = torch.zeros(lib.stb_decode_state_bytes(model._h, B), dtype=torch.uint8, device=dev)
-        self.ws = torch.empty(lib.stb_decode_ws_bytes(model._h, B), dtype=torch.uint8, device=dev)
+        self.ws = torch.zeros(lib.stb_decode_ws_bytes(model._h, B), dtype=torch.uint8, device=dev)   # tickets start at 0
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.logits = torch.empty(B, self.ldv, dtype=torch.float32, device=dev)
         self.seq = torch.zeros(B, 6, dtype=torch.int32, device=dev)          # stb_seq_state[B]
