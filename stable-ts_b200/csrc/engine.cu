@@ -434,10 +434,10 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     STB_TRY(embed_step(tokens, pos, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
     const void* emb_hi = t[STB_T_DEC_TOKEMB][0];
     const void* emb_lo = m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr;
-    // B <= 16: latency-optimised batched GEMV (mma.sync path, gemv.cu); larger batches: the tcgen05 GEMM core
+    // B <= 64: latency-optimised batched GEMV (mma.sync path, gemv.cu, 16 sequences per CTA); larger: the tcgen05 GEMM core
     auto lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
                    const float* res, float* out_f32, Split out_split, long long ld) -> int {
-        if (B <= 16)
+        if (B <= 64)
             return gemv(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st);
         stb_epilogue e;
         memset(&e, 0, sizeof(e));

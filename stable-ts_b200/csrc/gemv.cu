@@ -1,4 +1,4 @@
-// Decode-step linear layers for B <= 16 sequences: out[b][n] = epi( sum_k W[n][k] * x[b][k] ).
+// Decode-step linear layers for B <= 64 sequences (groups of 16 rows per CTA): out[b][n] = epi( sum_k W[n][k] * x[b][k] ).
 //
 // With M = B <= 16 rows every weight byte is used once: the op is a batched GEMV bound by HBM (d*d*4 B of weights in
 // parity mode), and its enemy is LATENCY, not FLOPs: a 6.5 MB matrix is 1 us of HBM time.  Design:
@@ -32,7 +32,7 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
 }
 
 __global__ void __launch_bounds__(GM_WARPS * 32, 2)
-gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, int B, int K,
+gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, int B, int K,   // B: total sequences
                 const __half* __restrict__ w_hi, const __half* __restrict__ w_lo, int N, const float* __restrict__ bias,
                 int act, const float* __restrict__ res, long long ld_res, float* __restrict__ out_f32,
                 __half* __restrict__ out_hi, __half* __restrict__ out_lo, long long ld_out) {
@@ -44,7 +44,13 @@ gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo
     float* red = reinterpret_cast<float*>(gsm + 32 * pitch); // [GM_WARPS][16][8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
-    const int n0 = blockIdx.x * 8;
+    // blockIdx.x = group of 16 sequences (fastest-varying: the CTAs sharing a weight tile run side by side, so the second
+    // group's weight reads hit L2), blockIdx.y = 8-feature tile
+    const int row0 = blockIdx.x * 16;
+    B = min(16, B - row0);
+    x_hi += (long long)row0 * K;
+    if (x_lo != nullptr) x_lo += (long long)row0 * K;
+    const int n0 = blockIdx.y * 8;
     const int n = n0 + g;
     const bool n_ok = n < N;
     const bool has_lo = w_lo != nullptr;
@@ -125,8 +131,8 @@ gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo
         if (row < B && nn < N) {
             if (bias != nullptr) v += __ldg(bias + nn);
             if (act == STB_ACT_GELU) v = gelu_erf(v);
-            if (res != nullptr) v += res[(long long)row * ld_res + nn];
-            const long long o = (long long)row * ld_out + nn;
+            if (res != nullptr) v += res[(long long)(row0 + row) * ld_res + nn];
+            const long long o = (long long)(row0 + row) * ld_out + nn;
             if (out_f32 != nullptr) out_f32[o] = v;
             if (out_hi != nullptr) {
                 __half hi, lo;
@@ -142,7 +148,7 @@ gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo
 int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, const void* w_lo, int N, const float* bias,
          int act, const float* res, long long ld_res, float* out_f32, void* out_hi, void* out_lo, long long ld_out,
          cudaStream_t st) {
-    STB_REQUIRE(B >= 1 && B <= 16 && K % 32 == 0 && K >= 32, "gemv: unsupported shape B=%d K=%d", B, K);
+    STB_REQUIRE(B >= 1 && B <= 64 && K % 32 == 0 && K >= 32, "gemv: unsupported shape B=%d K=%d", B, K);
     const int kc = K < GM_KC ? K : GM_KC;
     const size_t smem = (size_t)32 * (kc * 2 + 64) + GM_WARPS * 128 * sizeof(float);
     static size_t configured = 0;
@@ -152,7 +158,7 @@ int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, con
         configured = want;
     }
     ProfScope ps("gemv_mma", st, (double)N * K * 2.0 * (w_lo ? 2 : 1) + (double)B * K * 4.0 + (double)B * N * 4.0, 2.0 * B * (double)N * K);
-    STB_CUDA_OK(launch_pdl(gemv_mma_kernel, dim3(cdiv(N, 8)), dim3(GM_WARPS * 32), smem, st, (const __half*)x_hi,
+    STB_CUDA_OK(launch_pdl(gemv_mma_kernel, dim3(cdiv(B, 16), cdiv(N, 8)), dim3(GM_WARPS * 32), smem, st, (const __half*)x_hi,
                            (const __half*)x_lo, B, K, (const __half*)w_hi, (const __half*)w_lo, N, bias, act, res, ld_res,
                            out_f32, (__half*)out_hi, (__half*)out_lo, ld_out));
     STB_LAUNCH_OK();

@@ -129,7 +129,7 @@ def test_transcribe_window_matches_reference_driver_fixture(name):
 
 
 def test_decode_large_batch_uses_tensor_core_step_and_matches_gemv_step():
-    """B > 16 takes the tcgen05 small-M path, B <= 16 the batched-GEMV path: same tokens for the same windows."""
+    """18 sequences = two 16-row groups of the batched-GEMV step (the second one ragged): same tokens as 3 sequences."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     from oracle import stable_path as SP
@@ -143,3 +143,20 @@ def test_decode_large_batch_uses_tensor_core_step_and_matches_gemv_step():
     for b in range(18):
         assert r18[b].tokens == r3[b % 3].tokens
         assert abs(r18[b].avg_logprob - r3[b % 3].avg_logprob) < 1e-4
+
+
+def test_decode_batch_above_64_takes_tcgen05_step():
+    """B > 64 falls to the tcgen05 small-M GEMM step; must agree with the batched-GEMV step on the same windows."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import stable_path as SP
+    from stable_ts_b200.decode import DecodingOptions, decode_windows
+    W, model, gm, tk = _mk("tiny.en", 8)
+    audios = torch.stack([SP.synth_audio(160000, seed=80 + i) for i in range(2)])
+    pad = torch.zeros(2, 480000)
+    pad[:, :160000] = audios
+    opt = DecodingOptions(sample_len=12)
+    r66, _ = decode_windows(gm, tk, gm.encode(gm.log_mel(pad.repeat(33, 1).cuda())), opt)
+    r2, _ = decode_windows(gm, tk, gm.encode(gm.log_mel(pad.cuda())), opt)
+    for b in range(66):
+        assert r66[b].tokens == r2[b % 2].tokens
