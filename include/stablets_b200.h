@@ -157,10 +157,10 @@ STB_API size_t stb_encoder_ws_bytes(const stb_model* m, int B);
 STB_API int stb_encoder_forward(stb_model* m, const float* mel, int B, float* xa_f32, void* xa_hi, void* xa_lo, void* ws,
                         size_t ws_bytes, void* stream);
 
-/* cross-attention K and V^T of every decoder layer, computed once per window (whisper's kv_cache for cross_attn). */
+/* cross-attention K (head-major) and V^T of every decoder layer, computed once per window (whisper's kv_cache for
+ * cross_attn).  decode_layout != 0 additionally writes the head-major copy of V that stb_decode_step streams. */
 STB_API size_t stb_cross_kv_bytes(const stb_model* m, int B);
-STB_API int stb_cross_kv(stb_model* m, const void* xa_hi, const void* xa_lo, int B, void* cross_kv, void* ws, size_t ws_bytes,
-                 void* stream);
+STB_API int stb_cross_kv(stb_model* m, const void* xa_hi, const void* xa_lo, int B, int decode_layout, void* cross_kv, void* stream);
 
 /* a3 teacher-forced decoder with cross-attention capture (stable_whisper/timing.py:50-61 under disable_sdpa).
  *   tokens [B][M] int32.  logits (nullable) [B*M][ld_logits] fp32.
@@ -210,8 +210,9 @@ STB_API int stb_qk_postprocess_new(const float* qk, int B, int LH, int M, long l
  *   jumps [B][R] int32 = first frame of every row on the path (clipped at 0).
  *   path (nullable) [B][2][R+F] int32 = (text_idx, time_idx) in forward order, path_len [B]. */
 STB_API size_t stb_dtw_smem_bytes(int R, int F);
+STB_API size_t stb_dtw_ws_bytes(int B, int R, int F);   /* transposed + skewed copy of the cost matrix */
 STB_API int stb_dtw(const float* x, int B, int R, int F, long long ldx, int negate, int32_t* jumps, int32_t* path,
-            int32_t* path_len, void* stream);
+            int32_t* path_len, void* ws, size_t ws_bytes, void* stream);
 
 /* a9 KV-cached decode (stable_whisper/decode.py:33-65; whisper PyTorchInference.logits + logit filters +
  *    GreedyDecoder.update).  One step = one decoder forward for the newest token of B sequences.

@@ -57,7 +57,7 @@ _SIGS = {
     "stb_encoder_ws_bytes": (c_size_t, [c_void_p, c_int]),
     "stb_encoder_forward": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "stb_cross_kv_bytes": (c_size_t, [c_void_p, c_int]),
-    "stb_cross_kv": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "stb_cross_kv": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "stb_decoder_ws_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "stb_decoder_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_longlong, c_void_p,
                                     POINTER(c_int32), c_int, c_void_p, c_size_t, c_void_p]),
@@ -78,7 +78,9 @@ _SIGS = {
     "stb_qk_postprocess_new": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_float, c_int, c_int,
                                        c_float, c_float, c_float, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p]),
     "stb_dtw_smem_bytes": (c_size_t, [c_int, c_int]),
-    "stb_dtw": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "stb_dtw_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "stb_dtw": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                        c_void_p]),
 }
 
 _lib = None

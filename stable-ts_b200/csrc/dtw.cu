@@ -9,7 +9,8 @@
 //     wavefront is kept with ONE shuffle per step (up = lane-1's previous value, diag = the up of the previous step);
 //   * warps are software-pipelined: warp w+1 consumes the last row of warp w through a small shared-memory ring
 //     (256 columns) guarded by two monotone progress counters -- no block-wide barrier in the sweep;
-//   * x is staged in registers one 32-step block ahead (skewed per lane so the register index is static);
+//   * x is pre-transposed and pre-skewed (xs[t][r] = x[r][t - r%32], dtw_skew_kernel) so every step of a warp is ONE
+//     coalesced 128-byte load, prefetched one 32-step block ahead into registers (static register index);
 //   * the trace is 2 bits per cell, packed 16 cells per word in shared memory (<= 169 KB), and the backtrack runs in
 //     the same kernel on one thread with the current trace word cached in a register.
 #include <math.h>
@@ -36,8 +37,8 @@ __device__ __forceinline__ void wait_ge(const volatile int* p, int need) {
 }
 
 __global__ void __launch_bounds__(DTW_MAX_ROWS, 1)
-dtw_kernel(const float* __restrict__ x, int R, int F, long long ldx, long long x_bstride, int negate,
-           int32_t* __restrict__ jumps, int32_t* __restrict__ path, int32_t* __restrict__ path_len) {
+dtw_kernel(const float* __restrict__ xs, int R, int F, int Rpad, int32_t* __restrict__ jumps, int32_t* __restrict__ path,
+           int32_t* __restrict__ path_len) {
     extern __shared__ uint32_t dsm[];
     const int TW = (F + 15) >> 4;                              // trace words per row
     const int NW = (R + 31) >> 5;
@@ -51,7 +52,9 @@ dtw_kernel(const float* __restrict__ x, int R, int F, long long ldx, long long x
     const int lane = threadIdx.x & 31;
     const int r = w * 32 + lane;
     const bool row_ok = r < R;
-    const float* xr_ptr = x + (long long)b * x_bstride + (long long)r * ldx;
+    // xs [B][F+32][Rpad]: xs[t][r] = cost[r][t - (r & 31)] (0 outside): lane l of a warp reads ONE coalesced 128-byte
+    // row per step instead of 32 scattered sectors (the skew of the wavefront is baked into the layout by dtw_skew_kernel)
+    const float* xcol = xs + (long long)b * (F + 32) * Rpad + r;
     const float INF = INFINITY;
 
     if (threadIdx.x < NW) {
@@ -71,17 +74,14 @@ dtw_kernel(const float* __restrict__ x, int R, int F, long long ldx, long long x
         const int n_blocks = (F + 31 + 31) >> 5;                      // ceil((F+31)/32)
         float xc[32], xn[32];
 #pragma unroll
-        for (int s = 0; s < 32; ++s) {
-            const int col = s - lane;
-            xc[s] = (row_ok && col >= 0 && col < F) ? xr_ptr[col] : 0.f;
-        }
+        for (int s = 0; s < 32; ++s) xc[s] = xcol[(long long)s * Rpad];
 #pragma unroll 1
         for (int kb = 0; kb < n_blocks; ++kb) {
             // prefetch the next block (skewed by lane): lands while this block's 32 dependent steps run
 #pragma unroll
             for (int s = 0; s < 32; ++s) {
-                const int col = (kb + 1) * 32 + s - lane;
-                xn[s] = (row_ok && col >= 0 && col < F) ? xr_ptr[col] : 0.f;
+                const int t2 = (kb + 1) * 32 + s;
+                xn[s] = (t2 < F + 32) ? xcol[(long long)t2 * Rpad] : 0.f;
             }
 #pragma unroll
             for (int s = 0; s < 32; ++s) {
@@ -110,8 +110,7 @@ dtw_kernel(const float* __restrict__ x, int R, int F, long long ldx, long long x
                     if (c0 < c1 && c0 < c2) { c = c0; code = 0u; }
                     else if (c1 < c0 && c1 < c2) { c = c1; code = 1u; }
                     else { c = c2; code = 2u; }
-                    const float xv = negate ? -xc[s] : xc[s];
-                    own = xv + c;
+                    own = xc[s] + c;
                     tacc |= code << ((j & 15) * 2);
                     if ((j & 15) == 15 || j == F - 1) {
                         trace[(size_t)r * TW + (j >> 4)] = tacc;
@@ -181,6 +180,28 @@ dtw_kernel(const float* __restrict__ x, int R, int F, long long ldx, long long x
     }
 }
 
+// xs[b][t][r] = (+-) x[b][r][t - (r & 31)], zero outside [0, F) and for r >= R.  Tile transpose through shared memory:
+// coalesced reads along frames, coalesced writes along rows.
+__global__ void __launch_bounds__(256) dtw_skew_kernel(const float* __restrict__ x, int R, int F, long long ldx, int Rpad,
+                                                       int negate, float* __restrict__ xs) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;     // source tile: rows r0.., columns c0..
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* src = x + (long long)b * R * ldx;
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        float v = 0.f;
+        if (r < R && c < F) v = src[(long long)r * ldx + c];
+        tile[i][tx] = negate ? -v : v;
+    }
+    __syncthreads();
+    float* dst = xs + (long long)b * (F + 32) * Rpad;
+    for (int i = ty; i < 32; i += 8) {                       // i = source column offset, tx = row offset (lane index)
+        const int c = c0 + i;
+        if (c < F) dst[(long long)(c + tx) * Rpad + r0 + tx] = tile[tx][i];    // t = c + (r & 31), r & 31 == tx
+    }
+}
+
 static size_t dtw_smem(int R, int F) {
     const int TW = (F + 15) >> 4, NW = (R + 31) >> 5;
     return (size_t)R * TW * 4 + (size_t)(NW > 1 ? NW - 1 : 0) * DTW_RING * 4 + (size_t)NW * 2 * 4 + 16;
@@ -190,9 +211,15 @@ static size_t dtw_smem(int R, int F) {
 
 extern "C" size_t stb_dtw_smem_bytes(int R, int F) { return stb::dtw_smem(R, F); }
 
+extern "C" size_t stb_dtw_ws_bytes(int B, int R, int F) {
+    const size_t Rpad = (size_t)((R + 31) / 32) * 32;
+    return (size_t)B * (F + 32) * Rpad * sizeof(float);
+}
+
 extern "C" int stb_dtw(const float* x, int B, int R, int F, long long ldx, int negate, int32_t* jumps, int32_t* path,
-                       int32_t* path_len, void* stream) {
-    STB_REQUIRE(x && jumps, "stb_dtw: null pointer");
+                       int32_t* path_len, void* ws, size_t ws_bytes, void* stream) {
+    STB_REQUIRE(x && jumps && ws, "stb_dtw: null pointer");
+    STB_REQUIRE(ws_bytes >= stb_dtw_ws_bytes(B, R, F), "stb_dtw: workspace too small");
     STB_REQUIRE(B >= 1 && R >= 1 && F >= 1 && R <= stb::DTW_MAX_ROWS && F <= 1504 && ldx >= F,
                 "stb_dtw: unsupported shape B=%d R=%d F=%d ld=%lld (R<=%d, F<=1504)", B, R, F, ldx, stb::DTW_MAX_ROWS);
     const size_t smem = stb::dtw_smem(R, F);
@@ -209,8 +236,13 @@ extern "C" int stb_dtw(const float* x, int B, int R, int F, long long ldx, int n
     }
     STB_REQUIRE(smem <= max_dyn, "stb_dtw: trace needs %zu B of shared memory (limit %zu)", smem, max_dyn);
     const int NW = (R + 31) / 32;
-    stb::ProfScope ps("dtw", (cudaStream_t)stream, (double)B * R * F * 4.0, (double)B * R * F);
-    stb::dtw_kernel<<<B, NW * 32, smem, (cudaStream_t)stream>>>(x, R, F, ldx, (long long)R * ldx, negate, jumps, path, path_len);
+    const int Rpad = NW * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    stb::ProfScope ps("dtw(+skew)", st, (double)B * R * F * 4.0 * 3, (double)B * R * F);
+    STB_CUDA_OK(cudaMemsetAsync(ws, 0, stb_dtw_ws_bytes(B, R, F), st));      // zero border (t - (r&31) outside [0,F))
+    stb::dtw_skew_kernel<<<dim3(stb::cdiv(F, 32), NW, B), 256, 0, st>>>(x, R, F, ldx, Rpad, negate, (float*)ws);
+    STB_LAUNCH_OK();
+    stb::dtw_kernel<<<B, NW * 32, smem, st>>>((const float*)ws, R, F, Rpad, jumps, path, path_len);
     STB_LAUNCH_OK();
     return STB_OK;
 }

@@ -253,7 +253,7 @@ static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split
     }
 }
 
-static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int B, void* out, cudaStream_t st) {
+static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int B, void* out, bool decode_layout, cudaStream_t st) {
     const stb_dims& D = m->dims;
     const int T = D.n_audio_ctx, d = D.n_text_state;
     STB_REQUIRE(D.n_audio_state == D.n_text_state, "cross_kv: audio/text widths differ");
@@ -272,9 +272,10 @@ static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int 
         }
         STB_TRY(project_vT(m, xa, B, T, d, offs(W_HI(L, STB_L_CKV_W), (long long)d * d), offs(W_LO(L, STB_L_CKV_W), (long long)d * d),
                            W_F32(L, STB_L_CKV_B) + d, vT, STB_KPAD, st));
-        // head-major copy of V for the decode-step kernel (contiguous per (sequence, head), same layout as K)
-        STB_TRY(v_headmajor(vT.hi, B * D.n_text_head, T, STB_KPAD, Vd.hi, st));
-        if (Vd.lo) STB_TRY(v_headmajor(vT.lo, B * D.n_text_head, T, STB_KPAD, Vd.lo, st));
+        if (decode_layout) {   // head-major copy of V for the decode-step kernel (contiguous per (sequence, head), like K)
+            STB_TRY(v_headmajor(vT.hi, B * D.n_text_head, T, STB_KPAD, Vd.hi, st));
+            if (Vd.lo) STB_TRY(v_headmajor(vT.lo, B * D.n_text_head, T, STB_KPAD, Vd.lo, st));
+        }
     }
     return STB_OK;
 }
@@ -573,13 +574,12 @@ extern "C" size_t stb_cross_kv_bytes(const stb_model* m, int B) {
     return m ? stb::cross_layout(m, B).layer_halfs * sizeof(__half) * m->dims.n_text_layer : 0;
 }
 
-extern "C" int stb_cross_kv(stb_model* m, const void* xa_hi, const void* xa_lo, int B, void* cross_kv, void* ws,
-                            size_t ws_bytes, void* stream) {
-    (void)ws; (void)ws_bytes;
+extern "C" int stb_cross_kv(stb_model* m, const void* xa_hi, const void* xa_lo, int B, int decode_layout, void* cross_kv,
+                            void* stream) {
     STB_REQUIRE(m && xa_hi && cross_kv && B >= 1, "stb_cross_kv: bad arguments");
     STB_REQUIRE(m->prec != STB_PREC_FP16X3 || xa_lo, "stb_cross_kv: xa_lo required in FP16X3 mode");
     STB_TRY(check_weights(m, false, true));
-    return stb::cross_kv(m, (const __half*)xa_hi, (const __half*)xa_lo, B, cross_kv, (cudaStream_t)stream);
+    return stb::cross_kv(m, (const __half*)xa_hi, (const __half*)xa_lo, B, cross_kv, decode_layout != 0, (cudaStream_t)stream);
 }
 
 extern "C" size_t stb_decoder_ws_bytes(const stb_model* m, int B, int M) { return m ? stb::carve_decoder(m, B, M, nullptr).bytes : 0; }

@@ -17,6 +17,7 @@
 //   warps 2..5  : epilogue: tcgen05.ld 32 lanes x 32 columns -> bias / GELU / residual / scale -> global
 //                 (fp32 row-major, split-fp16 row-major, or either transposed).
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 #include <vector>
@@ -461,6 +462,10 @@ int gemm(const stb_operand& A, const stb_operand& B, int n_batch, int n_head, co
     const int passes = A.lo ? 3 : 1;
     const int N = B.rows;
     int BN = N <= 16 ? 16 : N <= 32 ? 32 : N <= 64 ? 64 : 128;
+    // 128 x 256 tiles: A 4 KB + B 8 KB of shared-memory reads per 128-cycle MMA (96 B/clk) instead of 128 B/clk -- the
+    // shared-memory port limit of a single-CTA 128 x 128 MMA.  Needs enough tiles to fill the SMs (env STB_GEMM_BN256=0 off).
+    static const bool bn256 = []() { const char* e = getenv("STB_GEMM_BN256"); return !(e && e[0] == '0'); }();
+    if (bn256 && N >= 256 && N % 256 == 0 && (long long)cdiv(N, 256) * cdiv(A.rows, 128) * n_batch * n_head >= 2LL * sm_count()) BN = 256;
     if (A.rows <= 128 && n_batch * n_head == 1) {
         // decode-step shape (M = batch of sequences): HBM-bound on the weights; use narrow N tiles so that enough CTAs
         // (>= ~120 of the 148 SMs) stream them concurrently
@@ -493,6 +498,7 @@ int gemm(const stb_operand& A, const stb_operand& B, int n_batch, int n_head, co
         STB_GEMM_CASE(32)
         STB_GEMM_CASE(64)
         STB_GEMM_CASE(128)
+        STB_GEMM_CASE(256)
     }
 #undef STB_GEMM_CASE
     return STB_ERR_UNSUPPORTED;

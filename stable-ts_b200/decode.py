@@ -128,7 +128,7 @@ def decode_windows(model: B200Whisper, tokenizer, enc: dict, options: Optional[D
     eng = StepEngine(model, B, steps)
     eng.reset()
     if ckv is None:
-        ckv = model.cross_kv(enc)
+        ckv = model.cross_kv(enc, decode=True)
     # filter tables (SuppressTokens, SuppressBlank)
     sup = torch.zeros(V, dtype=torch.uint8)
     sup[_suppress_list(tokenizer, options)] = 1 if options.suppress_tokens else 0

@@ -236,10 +236,11 @@ class B200Whisper:
                                               L.stream_ptr()))
         return {"f32": xa, "hi": hi, "lo": lo, "B": B}
 
-    def cross_kv(self, enc: Dict[str, torch.Tensor]) -> torch.Tensor:
+    def cross_kv(self, enc: Dict[str, torch.Tensor], decode: bool = False) -> torch.Tensor:
+        """Cross-attention K / V^T of every decoder layer; ``decode=True`` also lays V out for the KV-cached decode step."""
         B = enc["B"]
         out = torch.empty(self._lib.stb_cross_kv_bytes(self._h, B), dtype=torch.uint8, device=self.device)
-        L.check(self._lib.stb_cross_kv(self._h, L.ptr(enc["hi"]), L.ptr(enc["lo"]), B, L.ptr(out), None, 0, L.stream_ptr()))
+        L.check(self._lib.stb_cross_kv(self._h, L.ptr(enc["hi"]), L.ptr(enc["lo"]), B, int(decode), L.ptr(out), L.stream_ptr()))
         return out
 
     # ---- a3 ----
@@ -333,8 +334,9 @@ class B200Whisper:
         jumps = torch.empty(B, R, dtype=torch.int32, device=self.device)
         path = torch.empty(B, 2, R + F, dtype=torch.int32, device=self.device) if want_path else None
         plen = torch.empty(B, dtype=torch.int32, device=self.device) if want_path else None
+        ws = self._buf("dtw", self._lib.stb_dtw_ws_bytes(B, R, F))
         L.check(self._lib.stb_dtw(L.ptr(matrix), B, R, F, matrix.stride(1), int(negate), L.ptr(jumps), L.ptr(path),
-                                  L.ptr(plen), L.stream_ptr()))
+                                  L.ptr(plen), L.ptr(ws), ws.numel(), L.stream_ptr()))
         return (jumps, path, plen) if want_path else jumps
 
 

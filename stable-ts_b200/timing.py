@@ -57,11 +57,20 @@ def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *
     """Device side of ``_compute_qks`` for a batch of windows.  Returns dict(enc, ckv, logits, qk, M, S, rows)."""
     B = len(jobs)
     if enc is None:
-        audio = torch.zeros(B, N_SAMPLES, dtype=torch.float32)
-        for i, j in enumerate(jobs):
-            a = j.audio.detach().float().flatten()[:N_SAMPLES]
-            audio[i, : a.numel()] = a
-        audio = audio.pin_memory().to(model.device, non_blocking=True)
+        first = jobs[0].audio
+        base = first._base if (first is not None and first._base is not None) else None
+        if (base is not None and base.ndim == 2 and base.shape == (B, N_SAMPLES) and base.dtype == torch.float32
+                and all(j.audio is not None and j.audio._base is base and j.audio.shape[-1] == N_SAMPLES for j in jobs)
+                and all(j.audio.data_ptr() == base[i].data_ptr() for i, j in enumerate(jobs))):
+            audio = base                                   # the windows are the rows of one [B, 480000] batch: no host copy
+        else:
+            audio = torch.zeros(B, N_SAMPLES, dtype=torch.float32)
+            for i, j in enumerate(jobs):
+                a = j.audio.detach().float().flatten()[:N_SAMPLES]
+                audio[i, : a.numel()] = a
+        if not audio.is_pinned():
+            audio = audio.pin_memory()
+        audio = audio.to(model.device, non_blocking=True)
         mel = model.log_mel(audio)                         # == log_mel_spectrogram(audio, padding=N_SAMPLES-n)
         enc = model.encode(mel)
     if ckv is None:                                        # cross K/V of the window batch (reused from the decode pass)

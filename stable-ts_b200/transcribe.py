@@ -70,14 +70,21 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
     """B independent <=30 s windows -> list (per window) of segment dicts with ``words``.
     ``enc`` (+ ``n_samples``) may be passed instead of ``audios`` when the encoder output is already on the device."""
     if enc is None:
-        B = len(audios)
-        batch = torch.zeros(B, N_SAMPLES, dtype=torch.float32)
-        n_samples = []
-        for i, a in enumerate(audios):
-            a = a.detach().float().flatten()[:N_SAMPLES]
-            batch[i, : a.numel()] = a
-            n_samples.append(int(a.numel()))
-        mel = model.log_mel(batch.pin_memory().to(model.device, non_blocking=True))
+        if torch.is_tensor(audios) and audios.ndim == 2 and audios.shape[1] == N_SAMPLES and audios.dtype == torch.float32:
+            batch = audios                                   # already a [B, 480000] batch (ideally pinned): no host copy
+            if n_samples is None:
+                n_samples = [N_SAMPLES] * batch.shape[0]
+        else:
+            B = len(audios)
+            batch = torch.zeros(B, N_SAMPLES, dtype=torch.float32)
+            n_samples = []
+            for i, a in enumerate(audios):
+                a = a.detach().float().flatten()[:N_SAMPLES]
+                batch[i, : a.numel()] = a
+                n_samples.append(int(a.numel()))
+        if not batch.is_pinned():
+            batch = batch.pin_memory()
+        mel = model.log_mel(batch.to(model.device, non_blocking=True))
         enc = model.encode(mel)
     B = enc["B"]
     n_samples = list(n_samples) if n_samples is not None else [N_SAMPLES] * B

@@ -196,8 +196,9 @@ def _dtw_gpu(L, x, negate=False, want_path=True):
     jumps = torch.empty(B, R, dtype=torch.int32, device="cuda")
     path = torch.empty(B, 2, R + F, dtype=torch.int32, device="cuda")
     plen = torch.empty(B, dtype=torch.int32, device="cuda")
-    L.check(L.lib().stb_dtw(L.ptr(x), B, R, F, x.stride(1), int(negate), L.ptr(jumps), L.ptr(path), L.ptr(plen),
-                            L.stream_ptr()))
+    ws = torch.empty(L.lib().stb_dtw_ws_bytes(B, R, F), dtype=torch.uint8, device="cuda")
+    L.check(L.lib().stb_dtw(L.ptr(x), B, R, F, x.stride(1), int(negate), L.ptr(jumps), L.ptr(path), L.ptr(plen), L.ptr(ws),
+                            ws.numel(), L.stream_ptr()))
     torch.cuda.synchronize()
     return jumps.cpu().numpy(), path.cpu().numpy(), plen.cpu().numpy()
 
