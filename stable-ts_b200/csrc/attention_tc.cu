@@ -238,39 +238,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
         for (int t = 0; t < NT; ++t) {
             const int i = NT + t, st = i & 1;
             mbar_wait(&s_full[st], (i >> 1) & 1, 32);
-            mbar_wait(&p_empty, (t & 1) ^ 1, 33);                        // P.V of tile t-1 has consumed the buffer
             tc_fence_after();
+            // exponentials + hi/lo split of this warp's 64 keys are computed into registers BEFORE waiting for the P
+            // buffer, so they overlap the P.V MMAs of the previous tile; the score buffer is released right after the loads
+            uint4 hi4[8], lo4[8];
+            const int kt0 = t * AT_BK + half * 64;
+            const bool full_tile = kt0 + 64 <= g.Mk;             // warp-uniform: no per-element key masking needed
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(TM_S0 + st * 128 + lane_off + half * 64 + c * 32, r);
                 tmem_ld_wait();
 #pragma unroll
-                for (int j8 = 0; j8 < 4; ++j8) {                         // 8 keys = one 16-byte swizzle chunk
+                for (int j8 = 0; j8 < 4; ++j8) {                 // 8 keys = one 16-byte swizzle chunk
                     __align__(16) __half hi8[8];
                     __align__(16) __half lo8[8];
 #pragma unroll
                     for (int e = 0; e < 8; ++e) {
                         const int j = j8 * 8 + e;
-                        const int key = t * AT_BK + half * 64 + c * 32 + j;
-                        const float p = (key < g.Mk) ? exp2f(fmaf(__uint_as_float(r[j]), sc, -m)) : 0.f;
+                        float p = exp2f(fmaf(__uint_as_float(r[j]), sc, -m));
+                        if (!full_tile && kt0 + c * 32 + j >= g.Mk) p = 0.f;
                         l += p;
                         split_f16(p, hi8[e], lo8[e]);
                     }
-                    // K-major SWIZZLE_128B: row r -> 128 B at r*128; 16-byte chunk index XOR (r & 7)
-                    const int chunk = c * 4 + j8;
-                    const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-                    *reinterpret_cast<uint4*>(p_hi + off) = *reinterpret_cast<const uint4*>(hi8);
-                    if (NPL == 2) *reinterpret_cast<uint4*>(p_lo + off) = *reinterpret_cast<const uint4*>(lo8);
+                    hi4[c * 4 + j8] = *reinterpret_cast<const uint4*>(hi8);
+                    lo4[c * 4 + j8] = *reinterpret_cast<const uint4*>(lo8);
                 }
             }
-            fence_proxy_async();                                         // generic-proxy stores -> visible to the MMA
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&p_full);
-                mbar_arrive(&s_empty[st]);
+            if (lane == 0) mbar_arrive(&s_empty[st]);            // scores consumed: Q.K^T of tile t+2 may overwrite them
+            mbar_wait(&p_empty, (t & 1) ^ 1, 33);                // P.V of tile t-1 has consumed the P buffer
+            // K-major SWIZZLE_128B: row r -> 128 B at r*128; 16-byte chunk index XOR (r & 7)
+#pragma unroll
+            for (int chunk = 0; chunk < 8; ++chunk) {
+                const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+                *reinterpret_cast<uint4*>(p_hi + off) = hi4[chunk];
+                if (NPL == 2) *reinterpret_cast<uint4*>(p_lo + off) = lo4[chunk];
             }
+            fence_proxy_async();                                 // generic-proxy stores -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full);
         }
         // ---------------- epilogue: O (TMEM cols 256..319) -> split fp16 -> attention output
         mbar_wait(&o_full, 0, 34);

@@ -1,4 +1,4 @@
-// Decode-step linear layers for B <= 64 sequences (groups of 16 rows per CTA): out[b][n] = epi( sum_k W[n][k] * x[b][k] ).
+// Decode-step linear layers for B <= 64 sequences (up to 4 groups of 16 rows per CTA share the register-resident weights): out[b][n] = epi( sum_k W[n][k] * x[b][k] ).
 //
 // With M = B <= 16 rows every weight byte is used once: the op is a batched GEMV bound by HBM (d*d*4 B of weights in
 // parity mode), and its enemy is LATENCY, not FLOPs: a 6.5 MB matrix is 1 us of HBM time.  Design:
@@ -31,8 +31,10 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+constexpr int GM_MAXGRP = 4;                // up to 64 sequences: 4 groups of 16 rows share the register-resident weights
+
 __global__ void __launch_bounds__(GM_WARPS * 32, 2)
-gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, int B, int K,   // B: total sequences
+gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo, int B, int K,
                 const __half* __restrict__ w_hi, const __half* __restrict__ w_lo, int N, const float* __restrict__ bias,
                 int act, const float* __restrict__ res, long long ld_res, float* __restrict__ out_f32,
                 __half* __restrict__ out_hi, __half* __restrict__ out_lo, long long ld_out) {
@@ -44,23 +46,21 @@ gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo
     float* red = reinterpret_cast<float*>(gsm + 32 * pitch); // [GM_WARPS][16][8]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, q = lane & 3;
-    // blockIdx.x = group of 16 sequences (fastest-varying: the CTAs sharing a weight tile run side by side, so the second
-    // group's weight reads hit L2), blockIdx.y = 8-feature tile
-    const int row0 = blockIdx.x * 16;
-    B = min(16, B - row0);
-    x_hi += (long long)row0 * K;
-    if (x_lo != nullptr) x_lo += (long long)row0 * K;
-    const int n0 = blockIdx.y * 8;
+    const int n0 = blockIdx.x * 8;
     const int n = n0 + g;
     const bool n_ok = n < N;
     const bool has_lo = w_lo != nullptr;
-    float c[4] = {0.f, 0.f, 0.f, 0.f};
+    const int ngrp = (B + 15) >> 4;
+    float c[GM_MAXGRP][4];
+#pragma unroll
+    for (int gi = 0; gi < GM_MAXGRP; ++gi) c[gi][0] = c[gi][1] = c[gi][2] = c[gi][3] = 0.f;
     pdl_trigger();                                           // the next kernel may start its own weight prefetch
 
     for (int kc0 = 0; kc0 < K; kc0 += GM_KC) {
         const int kc = min(GM_KC, K - kc0);
         const int nblk = kc >> 5;
-        // ---- 1. all weight loads of this chunk in flight (block index = warp + i * GM_WARPS) ----
+        // ---- 1. all weight loads of this chunk in flight (block index = warp + i * GM_WARPS); they stay in registers
+        //         and are reused by every group of 16 sequences ----
         uint4 wh[GM_MAXBLK], wl[GM_MAXBLK];
 #pragma unroll
         for (int i = 0; i < GM_MAXBLK; ++i) {
@@ -73,72 +73,84 @@ gemv_mma_kernel(const __half* __restrict__ x_hi, const __half* __restrict__ x_lo
                 if (has_lo) wl[i] = __ldg(reinterpret_cast<const uint4*>(w_lo + off));
             }
         }
-        // ---- 2. stage x[:, kc0:kc0+kc] (16 rows; rows >= B are zero) ----
         if (kc0 == 0) pdl_wait();                            // weights are constants; x / res / out belong to predecessors
-        if (kc0 > 0) __syncthreads();                        // previous chunk's fragment reads are done
-        // cp.async (LDGSTS): every 16-byte piece of the tile is in flight at once, no registers, zero-fill for rows >= B
         const int vec_per_row = kc >> 3;                     // 16-byte pieces per row
-        for (int i = threadIdx.x; i < 16 * vec_per_row; i += blockDim.x) {
-            const int r = i / vec_per_row, v = i - r * vec_per_row;
-            const bool ok = r < B;
-            const long long off = (long long)(ok ? r : 0) * K + kc0 + v * 8;
-            const uint32_t dh = smem_u32(xs_hi + r * pitch + v * 16);
-            const uint32_t dl = smem_u32(xs_lo + r * pitch + v * 16);
-            const int nbytes_h = ok ? 16 : 0;
-            const int nbytes_l = (ok && x_lo != nullptr) ? 16 : 0;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dh), "l"(x_hi + off), "r"(nbytes_h) : "memory");
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dl), "l"((x_lo != nullptr ? x_lo : x_hi) + off),
-                         "r"(nbytes_l)
-                         : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        // ---- 3. MMAs: k inside a 32-block is permuted so that uint4 {x,y | z,w} are the two k16 steps ----
 #pragma unroll
-        for (int i = 0; i < GM_MAXBLK; ++i) {
-            const int blk = warp + i * GM_WARPS;
-            if (blk < nblk) {
-                const int col = (blk * 32 + q * 8) * 2;      // byte offset inside the row
-                const uint4 ah0 = *reinterpret_cast<const uint4*>(xs_hi + g * pitch + col);
-                const uint4 ah1 = *reinterpret_cast<const uint4*>(xs_hi + (g + 8) * pitch + col);
-                mma16816(c, ah0.x, ah1.x, ah0.y, ah1.y, wh[i].x, wh[i].y);
-                mma16816(c, ah0.z, ah1.z, ah0.w, ah1.w, wh[i].z, wh[i].w);
-                if (has_lo) {
-                    mma16816(c, ah0.x, ah1.x, ah0.y, ah1.y, wl[i].x, wl[i].y);
-                    mma16816(c, ah0.z, ah1.z, ah0.w, ah1.w, wl[i].z, wl[i].w);
-                    const uint4 al0 = *reinterpret_cast<const uint4*>(xs_lo + g * pitch + col);
-                    const uint4 al1 = *reinterpret_cast<const uint4*>(xs_lo + (g + 8) * pitch + col);
-                    mma16816(c, al0.x, al1.x, al0.y, al1.y, wh[i].x, wh[i].y);
-                    mma16816(c, al0.z, al1.z, al0.w, al1.w, wh[i].z, wh[i].w);
+        for (int gi = 0; gi < GM_MAXGRP; ++gi) {
+            if (gi < ngrp) {
+                const int row0 = gi * 16;
+                const int rows = min(16, B - row0);
+                // ---- 2. stage x[row0 : row0+16, kc0 : kc0+kc] with cp.async (zero-fill for absent rows) ----
+                if (kc0 > 0 || gi > 0) __syncthreads();      // the previous tile's fragment reads are done
+                for (int i = threadIdx.x; i < 16 * vec_per_row; i += blockDim.x) {
+                    const int r = i / vec_per_row, v = i - r * vec_per_row;
+                    const bool ok = r < rows;
+                    const long long off = (long long)(row0 + (ok ? r : 0)) * K + kc0 + v * 8;
+                    const uint32_t dh = smem_u32(xs_hi + r * pitch + v * 16);
+                    const uint32_t dl = smem_u32(xs_lo + r * pitch + v * 16);
+                    const int nbytes_h = ok ? 16 : 0;
+                    const int nbytes_l = (ok && x_lo != nullptr) ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dh), "l"(x_hi + off), "r"(nbytes_h) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dl),
+                                 "l"((x_lo != nullptr ? x_lo : x_hi) + off), "r"(nbytes_l)
+                                 : "memory");
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                __syncthreads();
+                // ---- 3. MMAs: k inside a 32-block is permuted so that uint4 {x,y | z,w} are the two k16 steps ----
+#pragma unroll
+                for (int i = 0; i < GM_MAXBLK; ++i) {
+                    const int blk = warp + i * GM_WARPS;
+                    if (blk < nblk) {
+                        const int col = (blk * 32 + q * 8) * 2;      // byte offset inside the row
+                        const uint4 ah0 = *reinterpret_cast<const uint4*>(xs_hi + g * pitch + col);
+                        const uint4 ah1 = *reinterpret_cast<const uint4*>(xs_hi + (g + 8) * pitch + col);
+                        mma16816(c[gi], ah0.x, ah1.x, ah0.y, ah1.y, wh[i].x, wh[i].y);
+                        mma16816(c[gi], ah0.z, ah1.z, ah0.w, ah1.w, wh[i].z, wh[i].w);
+                        if (has_lo) {
+                            mma16816(c[gi], ah0.x, ah1.x, ah0.y, ah1.y, wl[i].x, wl[i].y);
+                            mma16816(c[gi], ah0.z, ah1.z, ah0.w, ah1.w, wl[i].z, wl[i].w);
+                            const uint4 al0 = *reinterpret_cast<const uint4*>(xs_lo + g * pitch + col);
+                            const uint4 al1 = *reinterpret_cast<const uint4*>(xs_lo + (g + 8) * pitch + col);
+                            mma16816(c[gi], al0.x, al1.x, al0.y, al1.y, wh[i].x, wh[i].y);
+                            mma16816(c[gi], al0.z, al1.z, al0.w, al1.w, wh[i].z, wh[i].w);
+                        }
+                    }
                 }
             }
         }
     }
-    // ---- 4. cross-warp reduction: lane holds D[g][2q,2q+1] (c0,c1) and D[g+8][2q,2q+1] (c2,c3) ----
-    float* rw = red + warp * 128;
-    rw[g * 8 + 2 * q] = c[0];
-    rw[g * 8 + 2 * q + 1] = c[1];
-    rw[(g + 8) * 8 + 2 * q] = c[2];
-    rw[(g + 8) * 8 + 2 * q + 1] = c[3];
-    __syncthreads();
-    if (threadIdx.x < 128) {
-        const int row = threadIdx.x >> 3, col = threadIdx.x & 7;
-        float v = 0.f;
+    // ---- 4. cross-warp reduction per group: lane holds D[g][2q,2q+1] (c0,c1) and D[g+8][2q,2q+1] (c2,c3) ----
 #pragma unroll
-        for (int w = 0; w < GM_WARPS; ++w) v += red[w * 128 + threadIdx.x];
-        const int nn = n0 + col;
-        if (row < B && nn < N) {
-            if (bias != nullptr) v += __ldg(bias + nn);
-            if (act == STB_ACT_GELU) v = gelu_erf(v);
-            if (res != nullptr) v += res[(long long)(row0 + row) * ld_res + nn];
-            const long long o = (long long)(row0 + row) * ld_out + nn;
-            if (out_f32 != nullptr) out_f32[o] = v;
-            if (out_hi != nullptr) {
-                __half hi, lo;
-                split_f16(v, hi, lo);
-                out_hi[o] = hi;
-                if (out_lo != nullptr) out_lo[o] = lo;
+    for (int gi = 0; gi < GM_MAXGRP; ++gi) {
+        if (gi < ngrp) {
+            __syncthreads();
+            float* rw = red + warp * 128;
+            rw[g * 8 + 2 * q] = c[gi][0];
+            rw[g * 8 + 2 * q + 1] = c[gi][1];
+            rw[(g + 8) * 8 + 2 * q] = c[gi][2];
+            rw[(g + 8) * 8 + 2 * q + 1] = c[gi][3];
+            __syncthreads();
+            if (threadIdx.x < 128) {
+                const int row = gi * 16 + (threadIdx.x >> 3), col = threadIdx.x & 7;
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < GM_WARPS; ++w) v += red[w * 128 + threadIdx.x];
+                const int nn = n0 + col;
+                if (row < B && nn < N) {
+                    if (bias != nullptr) v += __ldg(bias + nn);
+                    if (act == STB_ACT_GELU) v = gelu_erf(v);
+                    if (res != nullptr) v += res[(long long)row * ld_res + nn];
+                    const long long o = (long long)row * ld_out + nn;
+                    if (out_f32 != nullptr) out_f32[o] = v;
+                    if (out_hi != nullptr) {
+                        __half hi, lo;
+                        split_f16(v, hi, lo);
+                        out_hi[o] = hi;
+                        if (out_lo != nullptr) out_lo[o] = lo;
+                    }
+                }
             }
         }
     }
@@ -158,7 +170,7 @@ int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, con
         configured = want;
     }
     ProfScope ps("gemv_mma", st, (double)N * K * 2.0 * (w_lo ? 2 : 1) + (double)B * K * 4.0 + (double)B * N * 4.0, 2.0 * B * (double)N * K);
-    STB_CUDA_OK(launch_pdl(gemv_mma_kernel, dim3(cdiv(B, 16), cdiv(N, 8)), dim3(GM_WARPS * 32), smem, st, (const __half*)x_hi,
+    STB_CUDA_OK(launch_pdl(gemv_mma_kernel, dim3(cdiv(N, 8)), dim3(GM_WARPS * 32), smem, st, (const __half*)x_hi,
                            (const __half*)x_lo, B, K, (const __half*)w_hi, (const __half*)w_lo, N, bias, act, res, ld_res,
                            out_f32, (__half*)out_hi, (__half*)out_lo, ld_out));
     STB_LAUNCH_OK();
