@@ -26,6 +26,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# one 30 s window keeps ~0.9 GB of fp32-grade cross K/V + KV cache resident: at 100+ windows per GPU the caching allocator must
+# not fragment (the cross-K/V block alone is > 80 GB)
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -382,7 +386,7 @@ def run_b200(args, dims_tuple):
         "metric": f"rtfx_{args.model}_{args.workload}", "value": value, "unit": "audio_s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 x3 split (fp32-grade), fp32 accumulate" if args.precision == "fp16x3" else "f16, fp32 accumulate",
-        "data": "synthetic",
+        "data": "synthetic", "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
         "config": {"workload": (f"transcribe+word_timestamps {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} forced "
                                 "KV-cached decode steps then word alignment (BASELINE configs 2/4 shape)") if args.workload == "transcribe"
                    else (f"align {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} text tokens/window "

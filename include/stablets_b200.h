@@ -108,6 +108,14 @@ STB_API int stb_attention(const stb_operand* q, const stb_operand* k, const stb_
                   int Mk, void* out_hi, void* out_lo, long long ld_out, long long out_h_stride, long long out_b_stride,
                   void* stream);
 
+/* Decode-step linear layer for B <= 64 sequences (batched GEMV, mma.sync + 4-CTA split-K cluster, csrc/gemv.cu):
+ * out[b][n] = act(sum_k W[n][k] x[b][k] + bias[n]) + res[b][n].  x split planes [B][K] (row pitch K), W split planes
+ * [N][K]; lo planes may be NULL (single pass).  K % 32 == 0.  Replaces torch.nn.functional.linear on the KV-cached decode
+ * path (whisper/model.py Linear.forward under stable_whisper/decode.py:27-40). */
+STB_API int stb_gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, const void* w_lo, int N,
+                     const float* bias, int act, const float* res, long long ld_res, float* out_f32, void* out_hi,
+                     void* out_lo, long long ld_out, void* stream);
+
 /* fp32 [rows][cols] (row pitch src_ld) -> split planes (row pitch dst_ld); lo may be NULL */
 STB_API int stb_split_f16(const float* src, long long rows, int cols, long long src_ld, void* hi, void* lo, long long dst_ld,
                   void* stream);

@@ -11,8 +11,10 @@
 //     (256 columns) guarded by two monotone progress counters -- no block-wide barrier in the sweep;
 //   * x is pre-transposed and pre-skewed (xs[t][r] = x[r][t - r%32], dtw_skew_kernel) so every step of a warp is ONE
 //     coalesced 128-byte load, prefetched one 32-step block ahead into registers (static register index);
-//   * the trace is 2 bits per cell, packed 16 cells per word in shared memory (<= 169 KB), and the backtrack runs in
-//     the same kernel on one thread with the current trace word cached in a register.
+//   * the sweep body is branch-free (~15 instructions per step): out-of-matrix cells are computed on zero-padded x and
+//     ignored, flow control sits at compile-time positions of the 32-step unrolled block;
+//   * the trace is 2 bits per cell, packed 16 STEPS per word (static bit position) in shared memory (<= 187 KB), and the
+//     backtrack runs in the same kernel on one thread with the current trace word cached in a register.
 #include <math.h>
 
 #include "common.cuh"
@@ -22,6 +24,10 @@ namespace stb {
 constexpr int DTW_RING = 256;                 // columns per inter-warp boundary ring
 constexpr int DTW_RING_CHUNKS = DTW_RING / 32;
 constexpr int DTW_MAX_ROWS = 480;             // 15 warps
+
+// Trace words per row: 16 steps per word over (Fpad/32 + 1) blocks of 32 steps, +1 to make the row pitch odd
+// (lanes store to the same word index of 32 consecutive rows: an odd pitch is conflict-free).
+__host__ __device__ __forceinline__ int dtw_trace_words(int F) { return (((F + 31) >> 5) + 1) * 2 + 1; }
 
 __device__ __forceinline__ int vload(const volatile int* p) { return *p; }
 // bounded spin on a monotone shared-memory progress counter (a protocol bug traps instead of hanging the box)
@@ -40,7 +46,7 @@ __global__ void __launch_bounds__(DTW_MAX_ROWS, 1)
 dtw_kernel(const float* __restrict__ xs, int R, int F, int Rpad, int32_t* __restrict__ jumps, int32_t* __restrict__ path,
            int32_t* __restrict__ path_len) {
     extern __shared__ uint32_t dsm[];
-    const int TW = (F + 15) >> 4;                              // trace words per row
+    const int TW = dtw_trace_words(F);                         // trace words per row (indexed by step t = j + lane)
     const int NW = (R + 31) >> 5;
     uint32_t* trace = dsm;                                     // [R][TW]
     volatile float* ring = reinterpret_cast<volatile float*>(trace + (size_t)R * TW);   // [NW-1][DTW_RING]
@@ -68,68 +74,87 @@ dtw_kernel(const float* __restrict__ xs, int R, int F, int Rpad, int32_t* __rest
         const bool is_cons = w > 0;
         const volatile float* ring_in = ring + (size_t)(w - 1) * DTW_RING;     // valid if is_cons
         volatile float* ring_out = ring + (size_t)w * DTW_RING;                // valid if is_prod
-        float own = INF;        // cost[r][j-1] (left)
-        float diag = INF;       // cost[r-1][j-1]
+        // Borders without per-step special cases: `own` (left) and `diag` start at +inf, which IS the j = 0 border
+        // (cost[i][0] = inf); only global row 0 sees cost[0][0] = 0 as its first diagonal.
+        float own = INF;                       // cost[r][j-1] (left)
+        float diag = (r == 0) ? 0.f : INF;     // cost[r-1][j-1]
         uint32_t tacc = 0;
-        const int n_blocks = (F + 31 + 31) >> 5;                      // ceil((F+31)/32)
+        const int Fpad = (F + 31) & ~31;                              // flow control works on whole 32-column chunks
+        const int n_blocks = (Fpad >> 5) + 1;                         // lane 31 reaches column Fpad - 1
+        const bool l0c = is_cons && lane == 0;                        // reads the ring
+        const bool l31p = is_prod && lane == 31;                      // writes the ring
+        uint32_t* trow = trace + (size_t)r * TW;
         float xc[32], xn[32];
 #pragma unroll
         for (int s = 0; s < 32; ++s) xc[s] = xcol[(long long)s * Rpad];
 #pragma unroll 1
         for (int kb = 0; kb < n_blocks; ++kb) {
-            // prefetch the next block (skewed by lane): lands while this block's 32 dependent steps run
+            // prefetch the next block: one coalesced 128-byte row per step, lands while the 32 dependent steps run
 #pragma unroll
             for (int s = 0; s < 32; ++s) {
                 const int t2 = (kb + 1) * 32 + s;
                 xn[s] = (t2 < F + 32) ? xcol[(long long)t2 * Rpad] : 0.f;
             }
+            const volatile float* rin_blk = ring_in + (kb & (DTW_RING_CHUNKS - 1)) * 32;
+            volatile float* rout_cur = ring_out + (kb & (DTW_RING_CHUNKS - 1)) * 32;
+            volatile float* rout_prev = ring_out + ((kb - 1) & (DTW_RING_CHUNKS - 1)) * 32;
+            // The step body is branch-free.  Cells outside the matrix (j < 0, j >= F, r >= R) are computed too: their x
+            // is 0 in the skewed buffer, so a lane that has not started keeps own = inf + 0, garbage past the right edge
+            // only flows to lanes that are past it as well, and their trace bits are never read by the backtrack.
 #pragma unroll
-            for (int s = 0; s < 32; ++s) {
+            for (int s = 0; s < 32; ++s) {                            // s is a compile-time constant in every copy
                 const int t = kb * 32 + s;                            // warp-uniform step
                 const int j = t - lane;                               // this lane's column
-                // ---- flow control (warp-uniform conditions) ----
-                if (is_cons && (t & 31) == 0 && t < F) {              // lane 0 is about to read ring chunk t/32
-                    const int need = (t >> 5) + 1;
-                    wait_ge(&prod[w - 1], need);
+                // ---- flow control, only at chunk edges (compile-time positions) ----
+                if (s == 0) {
+                    if (is_cons && t < Fpad) wait_ge(&prod[w - 1], (t >> 5) + 1);   // lane 0 reads ring chunk t/32 next
                 }
-                if (is_prod) {
-                    const int jp = t - 31;                            // lane 31's column
-                    if (jp >= 0 && (jp & 31) == 0 && jp < F) {        // about to overwrite ring chunk (jp/32) % CHUNKS
-                        const int need = (jp >> 5) - (DTW_RING_CHUNKS - 1);
-                        wait_ge(&cons[w + 1], need);
-                    }
+                if (s == 31) {
+                    const int jp = t - 31;                            // lane 31's column: start of its chunk jp/32
+                    if (is_prod && jp < Fpad) wait_ge(&cons[w + 1], (jp >> 5) - (DTW_RING_CHUNKS - 1));
                 }
-                float up = __shfl_up_sync(0xffffffffu, own, 1);
-                if (lane == 0) up = (is_cons && t < F) ? ring_in[t & (DTW_RING - 1)] : INF;
-                if (row_ok && j >= 0 && j < F) {
-                    const float c0 = (j == 0) ? (r == 0 ? 0.f : INF) : diag;
-                    const float c1 = up;
-                    const float c2 = (j == 0) ? INF : own;
-                    float c;
-                    uint32_t code;
-                    if (c0 < c1 && c0 < c2) { c = c0; code = 0u; }
-                    else if (c1 < c0 && c1 < c2) { c = c1; code = 1u; }
-                    else { c = c2; code = 2u; }
-                    own = xc[s] + c;
-                    tacc |= code << ((j & 15) * 2);
-                    if ((j & 15) == 15 || j == F - 1) {
-                        trace[(size_t)r * TW + (j >> 4)] = tacc;
-                        tacc = 0;
-                    }
-                    if (is_prod && lane == 31) ring_out[j & (DTW_RING - 1)] = own;
+                float rv = INF;
+                if (l0c && t < F) rv = rin_blk[s];                    // == ring_in[t & (DTW_RING - 1)]
+                const float sh = __shfl_up_sync(0xffffffffu, own, 1);
+                const float up = (lane == 0) ? rv : sh;
+                // 3-way strict-'<' selection + trace bits in one PTX block (keeps the two predicates next to their uses;
+                // left to the compiler, the 32 predicate pairs get parked in a register and unpacked 16 steps later).
+                // trace bits = (p0, p1): 1 diagonal, 2 up, 0 left; indexed by STEP, so the bit position is static.
+                float c;
+                asm volatile(
+                    "{\n\t.reg .pred p0, p1;\n\t.reg .f32 m;\n\t"
+                    "setp.lt.f32 p0, %2, %4;\n\t"
+                    "setp.lt.and.f32 p0, %2, %3, p0;\n\t"          // diagonal: c0 < c2 && c0 < c1
+                    "setp.lt.f32 p1, %3, %4;\n\t"
+                    "setp.lt.and.f32 p1, %3, %2, p1;\n\t"          // up: c1 < c2 && c1 < c0
+                    "selp.f32 m, %3, %4, p1;\n\t"
+                    "selp.f32 %0, %2, m, p0;\n\t"
+                    "@p0 add.u32 %1, %1, %5;\n\t"
+                    "@p1 add.u32 %1, %1, %6;\n\t}"
+                    : "=f"(c), "+r"(tacc)
+                    : "f"(diag), "f"(up), "f"(own), "r"(1u << ((s & 15) * 2)), "r"(2u << ((s & 15) * 2)));
+                own = xc[s] + c;
+                if (l31p && (unsigned)j < (unsigned)F) {              // lane 31: j = t - 31 -> ring_out[j & (DTW_RING - 1)]
+                    if (s == 31) rout_cur[0] = own; else rout_prev[s + 1] = own;
                 }
                 diag = up;
-                // ---- publish progress ----
-                if (is_prod) {
-                    const int jp = t - 31;
-                    if (jp >= 0 && jp < F && ((jp & 31) == 31 || jp == F - 1)) {
+                if ((s & 15) == 15) {
+                    if (row_ok) trow[t >> 4] = tacc;
+                    tacc = 0;
+                }
+                // ---- publish progress at chunk ends ----
+                if (s == 30) {
+                    const int jp = t - 31;                            // lane 31 just finished column jp, jp & 31 == 31
+                    if (is_prod && jp >= 0 && jp < Fpad) {
                         __threadfence_block();
                         if (lane == 31) prod[w] = (jp >> 5) + 1;
                     }
                 }
-                if (is_cons && t < F && ((t & 31) == 31 || t == F - 1)) {
-                    __threadfence_block();
-                    if (lane == 0) cons[w] = (t >> 5) + 1;
+                if (s == 31) {
+                    if (is_cons && t < Fpad) {
+                        __threadfence_block();
+                        if (lane == 0) cons[w] = (t >> 5) + 1;
+                    }
                 }
             }
 #pragma unroll
@@ -155,13 +180,14 @@ dtw_kernel(const float* __restrict__ xs, int R, int F, int Rpad, int32_t* __rest
             if (i == 0) code = 2u;                             // trace[0, :] = 2
             else if (j == 0) code = 1u;                        // trace[:, 0] = 1
             else {
-                const int rr = i - 1, cc = j - 1;
-                if (rr != cached_row || (cc >> 4) != cached_word) {
+                const int rr = i - 1, tt = j - 1 + ((i - 1) & 31);      // cell (rr, cc) was computed at step cc + lane
+                if (rr != cached_row || (tt >> 4) != cached_word) {
                     cached_row = rr;
-                    cached_word = cc >> 4;
+                    cached_word = tt >> 4;
                     word = trace[(size_t)rr * TW + cached_word];
                 }
-                code = (word >> ((cc & 15) * 2)) & 3u;
+                const uint32_t bits = (word >> ((tt & 15) * 2)) & 3u;   // (p0, p1) of the sweep
+                code = bits == 1u ? 0u : (bits == 2u ? 1u : 2u);
             }
             if (code == 0u) { --i; --j; }
             else if (code == 1u) { --i; }
@@ -203,7 +229,7 @@ __global__ void __launch_bounds__(256) dtw_skew_kernel(const float* __restrict__
 }
 
 static size_t dtw_smem(int R, int F) {
-    const int TW = (F + 15) >> 4, NW = (R + 31) >> 5;
+    const int TW = dtw_trace_words(F), NW = (R + 31) >> 5;
     return (size_t)R * TW * 4 + (size_t)(NW > 1 ? NW - 1 : 0) * DTW_RING * 4 + (size_t)NW * 2 * 4 + 16;
 }
 

@@ -403,8 +403,12 @@ struct StepWs {
     float* xpart;      // cross-attention split partials + tickets
     int* tickets;
     Split ln, attn, hid;
+    float* part;       // split-K partials [split][B][N] of the swapped tcgen05 decode linears
     size_t bytes;
 };
+constexpr int STEP_GEMV_MAX_B = 16;      // <= : mma.sync batched GEMV; above (up to 64): swapped split-K tcgen05 GEMM
+constexpr int STEP_SPLITK_MAX_B = 128;    // sequences on the N side of one tcgen05 tile (BN = 16 / 32 / 64 / 128)
+constexpr int STEP_SPLITK_TILES = 160;   // bound on split * ceil(N / 128) (one tile per SM)
 static StepWs carve_step(const stb_model* m, int B, void* ws) {
     const bool lo = m->prec == STB_PREC_FP16X3;
     const size_t d = m->dims.n_text_state;
@@ -418,6 +422,7 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.ln = take_split(c, (size_t)B * d, lo);
     w.attn = take_split(c, (size_t)B * d, lo);
     w.hid = take_split(c, (size_t)B * 4 * d, lo);
+    w.part = (B > STEP_GEMV_MAX_B && B <= STEP_SPLITK_MAX_B) ? c.take<float>((size_t)B * STEP_SPLITK_TILES * 128) : nullptr;
     w.bytes = c.off;
     return w;
 }
@@ -435,44 +440,92 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     STB_TRY(embed_step(tokens, pos, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
     const void* emb_hi = t[STB_T_DEC_TOKEMB][0];
     const void* emb_lo = m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr;
-    // B <= 64: latency-optimised batched GEMV (mma.sync path, gemv.cu, 16 sequences per CTA); larger: the tcgen05 GEMM core
-    auto lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
-                   const float* res, float* out_f32, Split out_split, long long ld) -> int {
-        if (B <= 64)
-            return gemv(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st);
-        stb_epilogue e;
-        memset(&e, 0, sizeof(e));
-        e.out_f32 = out_f32; e.out_hi = out_split.hi; e.out_lo = out_split.lo; e.ld_out = ld;
-        e.bias = bias; e.act = act; e.residual = res; e.ld_res = ld; e.alpha = 1.0f;
-        return linear(m, x, B, k, w_hi, w_lo, n, e, st);
-    };
+    // Linear layers of the step, by batch size:
+    //   B <= 16      : latency-optimised batched GEMV (mma.sync, gemv.cu) -- one launch, weights straight into fragments
+    //   17 .. 128    : SWAPPED split-K tcgen05 GEMM: the features take the 128-row M side (every weight byte is read by
+    //                  exactly one CTA), the sequences the N side (BN = 32/64/128), and the K range is cut into `split`
+    //                  slices on the GEMM batch axis so that ~one tile lands on every SM; partials [split][B][N] stay in
+    //                  L2 and splitk_finish_kernel adds bias / GELU / residual and the LayerNorm that follows
+    //   > 128        : the plain tcgen05 GEMM (sequences on the M side)
+    const bool use_gemv = B <= STEP_GEMV_MAX_B, use_splitk = !use_gemv && B <= STEP_SPLITK_MAX_B;
     const Split none = {nullptr, nullptr};
+    // ln_g != nullptr: also produce LayerNorm(out)*ln_g+ln_b into w.ln (only with a residual, out_f32 = w.x)
+    auto lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
+                   const float* res, float* out_f32, Split out_split, long long ld, const float* ln_g,
+                   const float* ln_b) -> int {
+        if (use_gemv) {
+            STB_TRY(gemv(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st));
+        } else if (use_splitk) {
+            const int mt = cdiv(n, 128), nkb = k / 64;
+            int split = 1;
+            if (k % 64 == 0)
+                for (int sdiv = 1; sdiv <= nkb; ++sdiv)
+                    if (nkb % sdiv == 0 && (long long)mt * sdiv <= sm_count() && mt * sdiv <= STEP_SPLITK_TILES) split = sdiv;
+            const bool direct = split == 1 && bias == nullptr && act == STB_ACT_NONE && res == nullptr && ln_g == nullptr &&
+                                out_split.hi == nullptr;
+            const int ks = k / split;
+            stb_operand a = {w_hi, w_lo, n, ks, (long long)k, 0, (long long)ks};
+            stb_operand b = {x.hi, x.lo, B, ks, (long long)k, 0, (long long)ks};
+            stb_epilogue e;
+            memset(&e, 0, sizeof(e));
+            e.transposed = 1;                                  // D is [feature][sequence]; store [sequence][feature]
+            e.alpha = 1.0f;
+            if (direct) {
+                e.out_f32 = out_f32;
+                e.ld_out = ld;
+                return gemm(a, b, 1, 1, e, st);
+            }
+            STB_REQUIRE((long long)mt * split <= STEP_SPLITK_TILES || split == 1, "decode_step: split-K workspace bound");
+            STB_REQUIRE((size_t)split * B * n <= (size_t)B * STEP_SPLITK_TILES * 128, "decode_step: split-K partials exceed the workspace");
+            e.out_f32 = w.part;
+            e.ld_out = n;
+            e.out_b_stride = (long long)B * n;
+            STB_TRY(gemm(a, b, split, 1, e, st));
+            return splitk_finish(w.part, split, B, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, ln_g, ln_b,
+                                 ln_g ? w.ln.hi : nullptr, ln_g ? w.ln.lo : nullptr, st);
+        } else {
+            stb_epilogue e;
+            memset(&e, 0, sizeof(e));
+            e.out_f32 = out_f32; e.out_hi = out_split.hi; e.out_lo = out_split.lo; e.ld_out = ld;
+            e.bias = bias; e.act = act; e.residual = res; e.ld_res = ld; e.alpha = 1.0f;
+            STB_TRY(linear(m, x, B, k, w_hi, w_lo, n, e, st));
+        }
+        if (ln_g != nullptr)                                   // paths without the fused finish: standalone LayerNorm
+            STB_TRY(layernorm(out_f32, B, n, ln_g, ln_b, w.ln.hi, w.ln.lo, nullptr, st));
+        return STB_OK;
+    };
+    const float* final_g = (const float*)t[STB_T_DEC_LN_G][0];
+    const float* final_b = (const float*)t[STB_T_DEC_LN_B][0];
+    if (D.n_text_layer > 0)
+        STB_TRY(layernorm(w.x, B, d, W_F32(m->dec[0], STB_L_ATTN_LN_G), W_F32(m->dec[0], STB_L_ATTN_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
+    else
+        STB_TRY(layernorm(w.x, B, d, final_g, final_b, w.ln.hi, w.ln.lo, nullptr, st));
     for (int l = 0; l < D.n_text_layer; ++l) {
         const stb_model::Layer& L = m->dec[l];
+        const bool last = l + 1 == D.n_text_layer;
+        const float* next_g = last ? final_g : W_F32(m->dec[l + 1], STB_L_ATTN_LN_G);
+        const float* next_b = last ? final_b : W_F32(m->dec[l + 1], STB_L_ATTN_LN_B);
         float* Kc = (float*)state + (size_t)l * 2 * cache;
         float* Vc = Kc + cache;
-        STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_ATTN_LN_G), W_F32(L, STB_L_ATTN_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
+        // w.ln holds attn_ln(x) here (previous layer's fc2 finish, or the standalone LayerNorm above)
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_QKV_W), W_LO(L, STB_L_QKV_W), 3 * d, W_F32(L, STB_L_QKV_B), STB_ACT_NONE, nullptr,
-                    w.qkv, none, 3 * d));
+                    w.qkv, none, 3 * d, nullptr, nullptr));
         STB_TRY(decode_attn_self(w.qkv, Kc, Vc, B, H, d, ctx, pos, w.attn.hi, w.attn.lo, nullptr, st));
         STB_TRY(lin(w.attn, d, W_HI(L, STB_L_OUT_W), W_LO(L, STB_L_OUT_W), d, W_F32(L, STB_L_OUT_B), STB_ACT_NONE, w.x, w.x,
-                    none, d));
-        STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_CROSS_LN_G), W_F32(L, STB_L_CROSS_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
+                    none, d, W_F32(L, STB_L_CROSS_LN_G), W_F32(L, STB_L_CROSS_LN_B)));
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_CQ_W), W_LO(L, STB_L_CQ_W), d, W_F32(L, STB_L_CQ_B), STB_ACT_NONE, nullptr, w.q,
-                    none, d));
+                    none, d, nullptr, nullptr));
         Split Kx, vTx, Vd;
         cross_ptrs(m, B, ckv, l, Kx, vTx, &Vd);
         STB_TRY(decode_attn_cross(w.q, Kx.hi, Kx.lo, Vd.hi, Vd.lo, B, H, d, w.xpart, w.tickets, w.attn.hi, w.attn.lo, nullptr, st));
         STB_TRY(lin(w.attn, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d, W_F32(L, STB_L_COUT_B), STB_ACT_NONE, w.x,
-                    w.x, none, d));
-        STB_TRY(layernorm(w.x, B, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
+                    w.x, none, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B)));
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_FC1_W), W_LO(L, STB_L_FC1_W), 4 * d, W_F32(L, STB_L_FC1_B), STB_ACT_GELU, nullptr,
-                    nullptr, w.hid, 4 * d));
+                    nullptr, w.hid, 4 * d, nullptr, nullptr));
         STB_TRY(lin(w.hid, 4 * d, W_HI(L, STB_L_FC2_W), W_LO(L, STB_L_FC2_W), d, W_F32(L, STB_L_FC2_B), STB_ACT_NONE, w.x, w.x,
-                    none, d));
+                    none, d, next_g, next_b));
     }
-    STB_TRY(layernorm(w.x, B, d, (const float*)t[STB_T_DEC_LN_G][0], (const float*)t[STB_T_DEC_LN_B][0], w.ln.hi, w.ln.lo, nullptr, st));
-    STB_TRY(lin(w.ln, d, emb_hi, emb_lo, D.n_vocab, nullptr, STB_ACT_NONE, nullptr, logits, none, ld_logits));
+    STB_TRY(lin(w.ln, d, emb_hi, emb_lo, D.n_vocab, nullptr, STB_ACT_NONE, nullptr, logits, none, ld_logits, nullptr, nullptr));
     STB_TRY(bump_pos(pos, st));
     return STB_OK;
 }

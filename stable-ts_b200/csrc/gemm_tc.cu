@@ -116,6 +116,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_slot;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped
+    // the tail of the previous kernel in the stream; its outputs (our operands / residual) are visible after the wait.
+    pdl_trigger();
+    pdl_wait();
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
@@ -448,7 +452,8 @@ static int launch_gemm(const TmapVal& ah, const TmapVal& al, const TmapVal& bh, 
         const double zz = (double)n_batch * g.H;
         ProfScope ps("gemm_tc", st, zz * ((double)g.M * g.K + (double)g.N * g.K) * 2.0 * Cfg::NPL + zz * (double)g.M * g.N * 4.0,
                      2.0 * g.M * (double)g.N * g.K * zz);
-        gemm_tc_kernel<BN, PASSES><<<grid, 192, Cfg::SMEM, st>>>(ah.map, al.map, bh.map, bl.map, g);
+        STB_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, PASSES>, grid, dim3(192), (size_t)Cfg::SMEM, st, ah.map, al.map, bh.map,
+                               bl.map, g));
     }
     STB_LAUNCH_OK();
     return STB_OK;

@@ -44,6 +44,9 @@ int v_headmajor(const __half* vT, int BH, int T, int Tp, __half* v, cudaStream_t
 int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, const void* w_lo, int N, const float* bias,
          int act, const float* res, long long ld_res, float* out_f32, void* out_hi, void* out_lo, long long ld_out,
          cudaStream_t st);
+int splitk_finish(const float* P, int split, int B, int N, const float* bias, int act, const float* res, long long ld_res,
+                  float* out_f32, void* out_hi, void* out_lo, long long ld_out, const float* ln_g, const float* ln_b,
+                  void* ln_hi, void* ln_lo, cudaStream_t st);
 int embed_step(const int32_t* tokens, const int32_t* pos, int B, int d, const float* emb, const float* posemb, float* x,
                cudaStream_t st);
 int bump_pos(int32_t* pos, cudaStream_t st);

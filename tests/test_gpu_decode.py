@@ -160,3 +160,41 @@ def test_decode_batch_above_64_takes_tcgen05_step():
     r2, _ = decode_windows(gm, tk, gm.encode(gm.log_mel(pad.cuda())), opt)
     for b in range(66):
         assert r66[b].tokens == r2[b % 2].tokens
+
+
+def test_large_width_step_paths_agree():
+    """large-v3 widths (d = 1280, 20 heads, 51866 tokens; 1 encoder + 2 decoder layers): the three decode-step linear
+    paths -- mma.sync GEMV (B = 2), swapped split-K tcgen05 GEMM + fused finish/LayerNorm (B = 20 and 50: BN = 32 / 64,
+    K = 1280 and 5120 splits, direct vocabulary projection) -- must produce the same step logits and tokens."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import stable_path as SP
+    from oracle.whisper_ref.model import ModelDimensions
+    from stable_ts_b200.decode import DecodingOptions, decode_windows
+    dims = ModelDimensions(n_mels=128, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=1, n_vocab=51866,
+                           n_text_ctx=448, n_text_state=1280, n_text_head=20, n_text_layer=2)
+    W, model, gm, tk = _mk(dims, 17)
+    audios = torch.stack([SP.synth_audio(480000, seed=90 + i) for i in range(2)])
+    enc2 = gm.encode(gm.log_mel(audios.cuda()))
+    steps = 5
+    opt = DecodingOptions(sample_len=steps)
+    r2, x2 = decode_windows(gm, tk, enc2, opt, return_step_logits=True)
+    V = dims.n_vocab
+    for rep in (10, 25):
+        encb = gm.encode(gm.log_mel(audios.repeat(rep, 1).cuda()))
+        rb, xb = decode_windows(gm, tk, encb, opt, return_step_logits=True)
+        worst = 0.0
+        for i in range(len(x2["step_logits"])):
+            a = x2["step_logits"][i].float().cpu()
+            b = xb["step_logits"][i].float().cpu()
+            fin = a > -1e30
+            for j in range(2 * rep):
+                assert torch.equal(fin[j % 2], b[j] > -1e30)
+                worst = max(worst, ((b[j][fin[j % 2]] - a[j % 2][fin[j % 2]]).abs().max() / a[j % 2][fin[j % 2]].abs().max()).item())
+        print(f"B={2 * rep} vs B=2 step logits: worst rel diff {worst:.2e}")
+        assert worst < 2e-5
+        for j in range(2 * rep):
+            assert rb[j].tokens == r2[j % 2].tokens
+        rg, _ = decode_windows(gm, tk, encb, opt)                     # CUDA-graph replay of the same step
+        for j in range(2 * rep):
+            assert rg[j].tokens == r2[j % 2].tokens

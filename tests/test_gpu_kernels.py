@@ -85,6 +85,64 @@ def test_gemm_plain(L, M, N, K, passes):
     assert err < (max(3e-6, 2e-7 * K ** 0.5 * 2) if passes == 3 else 3e-3)   # grows ~sqrt(K)
 
 
+def _gemv(L, X, W, passes=3, bias=None, act=0, residual=None, out="f32"):
+    """X [B,K], W [N,K] fp32 cuda -> act(X W^T + bias) + residual via stb_gemv (decode-step linear)."""
+    Bn, K = X.shape
+    N = W.shape[0]
+    xh, xl = _split(X, passes == 3)
+    wh, wl = _split(W, passes == 3)
+    ld = (N + 7) // 8 * 8
+    of = torch.full((Bn, ld), float("nan"), device="cuda") if out == "f32" else None
+    oh = torch.zeros(Bn, ld, dtype=torch.float16, device="cuda") if out == "split" else None
+    ol = torch.zeros(Bn, ld, dtype=torch.float16, device="cuda") if out == "split" else None
+    L.check(L.lib().stb_gemv(L.ptr(xh), L.ptr(xl), Bn, K, L.ptr(wh), L.ptr(wl), N, L.ptr(bias), act, L.ptr(residual),
+                             residual.stride(0) if residual is not None else 0, L.ptr(of), L.ptr(oh), L.ptr(ol), ld,
+                             L.stream_ptr()))
+    torch.cuda.synchronize()
+    return of[:, :N] if out == "f32" else oh[:, :N].float() + ol[:, :N].float()
+
+
+@pytest.mark.parametrize("Bn,N,K", [(64, 1280, 1280), (50, 1280, 5120), (33, 5120, 1280), (16, 3840, 1280), (1, 384, 384),
+                                    (7, 1002, 384), (18, 384, 1536), (3, 130, 128), (64, 51866, 128), (40, 512, 2048)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_gemv_decode_linear_vs_fp64(L, Bn, N, K, passes):
+    """every width of the Whisper family (K = 128 .. 5120: one or several K chunks, odd/even slices per CTA, idle cluster
+    ranks), ragged sequence groups and a ragged last feature tile"""
+    g = torch.Generator(device="cuda").manual_seed(Bn * 31 + N + K)
+    X = torch.randn(Bn, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.3
+    D = _gemv(L, X, W, passes).double().cpu()
+    R = _ref(X, W)
+    err = (D - R).abs().max().item() / R.abs().max().item()
+    print(f"gemv B={Bn} N={N} K={K} passes={passes}: rel err {err:.3e}")
+    assert torch.isfinite(D).all()
+    assert err < (max(3e-6, 2e-7 * K ** 0.5 * 2) if passes == 3 else 3e-3)
+
+
+def test_gemv_epilogues_and_in_place_residual(L):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    Bn, N, K = 37, 640, 1280
+    X = torch.randn(Bn, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g) * 0.2
+    bias = torch.randn(N, device="cuda", generator=g)
+    res = torch.randn(Bn, N, device="cuda", generator=g)
+    for kw in [dict(bias=bias), dict(bias=bias, act=1), dict(bias=bias, residual=res), dict(bias=bias, act=1, residual=res)]:
+        D = _gemv(L, X, W, 3, **kw).double().cpu()
+        R = _ref(X, W, **kw)
+        assert (D - R).abs().max().item() / R.abs().max().item() < 5e-6
+    D = _gemv(L, X, W, 3, bias=bias, act=1, out="split").double().cpu()
+    assert (D - _ref(X, W, bias=bias, act=1)).abs().max().item() / _ref(X, W, bias=bias, act=1).abs().max().item() < 5e-6
+    # the decoder's residual stream is updated in place: out_f32 == res
+    xh, xl = _split(X)
+    wh, wl = _split(W)
+    stream = res.clone()
+    L.check(L.lib().stb_gemv(L.ptr(xh), L.ptr(xl), Bn, K, L.ptr(wh), L.ptr(wl), N, L.ptr(bias), 0, L.ptr(stream), N,
+                             L.ptr(stream), None, None, N, L.stream_ptr()))
+    torch.cuda.synchronize()
+    R = _ref(X, W, bias=bias, residual=res)
+    assert (stream.double().cpu() - R).abs().max().item() / R.abs().max().item() < 5e-6
+
+
 def test_gemm_epilogues(L):
     g = torch.Generator(device="cuda").manual_seed(5)
     M, N, K = 333, 264, 448
