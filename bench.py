@@ -47,7 +47,8 @@ def parse():
     p.add_argument("--workload", default="transcribe", choices=["transcribe", "align"],
                    help="transcribe: 224 forced KV-cached decode steps + word timestamps (BASELINE configs 2/4 shape); "
                         "align: forced alignment of a 100-token script (configs 1/3 shape)")
-    p.add_argument("--windows", type=int, default=64, help="30 s windows per GPU per step")
+    p.add_argument("--windows", type=int, default=120,
+                   help="30 s windows per GPU per step (120 = one rank's share of BASELINE config 4: 8 h of audio over 8 GPUs)")
     p.add_argument("--tokens", type=int, default=None, help="text tokens per window (default: 224 transcribe / 100 align)")
     p.add_argument("--precision", default="fp16x3", choices=["fp16x3", "fp16"])
     p.add_argument("--cpu-windows", type=int, default=1, help="windows in the bounded CPU-baseline sample")
@@ -387,6 +388,8 @@ def run_b200(args, dims_tuple):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 x3 split (fp32-grade), fp32 accumulate" if args.precision == "fp16x3" else "f16, fp32 accumulate",
         "data": "synthetic", "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+        "allocator": {k: int(torch.cuda.memory_stats().get(k, 0)) for k in ("num_alloc_retries", "num_ooms", "num_device_alloc",
+                                                                               "num_device_free")},
         "config": {"workload": (f"transcribe+word_timestamps {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} forced "
                                 "KV-cached decode steps then word alignment (BASELINE configs 2/4 shape)") if args.workload == "transcribe"
                    else (f"align {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} text tokens/window "

@@ -18,16 +18,19 @@ namespace stb {
 // ---------------------------------------------------------------------------------------------------------
 // self-attention over the fp32 K/V cache.  grid (H, B), 128 threads.
 //   qkv [B][3d] fp32 (q | k | v of the newest token); caches Kc, Vc [B][ctx][d] fp32; out split [B][d].
+// One pass, flash-decoding style (same lane mapping as the cross-attention kernel below): 8 lanes share a key row
+// (2 x 16-byte loads of K and of V per lane), 4 keys per warp load, 4 keys in flight per lane group, online softmax per
+// lane group, the 16 lane groups of the CTA merged through shared memory.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, float* __restrict__ Vc, int d, int ctx,
                         const int32_t* __restrict__ pos_ptr, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
                         float* __restrict__ out_f32) {
-    __shared__ float s_q[64];
-    __shared__ float s_p[448 + 32];
-    __shared__ float s_red[4];
-    __shared__ float s_o[2][64];
+    __shared__ float s_m[4][4], s_l[4][4];
+    __shared__ float s_acc[4][4][64];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int w = tid >> 5, lane = tid & 31;
+    const int sub = lane & 7, grp = lane >> 3;
     pdl_trigger();
     pdl_wait();
     const int pos = *pos_ptr;
@@ -35,49 +38,69 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
     const float* row = qkv + (long long)b * 3 * d;
     float* kc = Kc + (long long)b * ctx * d + h * 64;
     float* vc = Vc + (long long)b * ctx * d + h * 64;
-    if (tid < 64) {
-        s_q[tid] = row[h * 64 + tid];
-        kc[(long long)pos * d + tid] = row[d + h * 64 + tid];
-    } else {
-        vc[(long long)pos * d + (tid - 64)] = row[2 * d + h * 64 + (tid - 64)];
-    }
-    __syncthreads();
-    float mx = -INFINITY;
-    for (int j = tid; j < n; j += 128) {
-        const float4* kr = reinterpret_cast<const float4*>(kc + (long long)j * d);
-        float acc = 0.f;
+    if (tid < 64) kc[(long long)pos * d + tid] = row[d + h * 64 + tid];
+    else vc[(long long)pos * d + (tid - 64)] = row[2 * d + h * 64 + (tid - 64)];
+    float qr[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            const float4 kv = kr[c];
-            acc = fmaf(s_q[4 * c], kv.x, acc); acc = fmaf(s_q[4 * c + 1], kv.y, acc);
-            acc = fmaf(s_q[4 * c + 2], kv.z, acc); acc = fmaf(s_q[4 * c + 3], kv.w, acc);
+    for (int e = 0; e < 8; ++e) qr[e] = row[h * 64 + sub * 8 + e] * 0.125f;
+    __syncthreads();                                         // the newest K / V row is visible to the whole CTA
+    float m = -INFINITY, l = 0.f, acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int base = 0; base < n; base += 64) {               // block-uniform trip count: 64 keys per CTA iteration
+        const int j0 = base + w * 4 + grp;
+        float4 ka[4], kb[4], va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * 16;
+            ka[u] = kb[u] = va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < n) {
+                const float4* kr = reinterpret_cast<const float4*>(kc + (long long)j * d + sub * 8);
+                const float4* vr = reinterpret_cast<const float4*>(vc + (long long)j * d + sub * 8);
+                ka[u] = kr[0]; kb[u] = kr[1];
+                va[u] = vr[0]; vb[u] = vr[1];
+            }
         }
-        acc *= 0.125f;
-        s_p[j] = acc;
-        mx = fmaxf(mx, acc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * 16;
+            float s = qr[0] * ka[u].x;
+            s = fmaf(qr[1], ka[u].y, s); s = fmaf(qr[2], ka[u].z, s); s = fmaf(qr[3], ka[u].w, s);
+            s = fmaf(qr[4], kb[u].x, s); s = fmaf(qr[5], kb[u].y, s); s = fmaf(qr[6], kb[u].z, s); s = fmaf(qr[7], kb[u].w, s);
+            s += __shfl_xor_sync(0xffffffffu, s, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4);
+            if (j < n) {                                      // uniform within the 8-lane group
+                const float mn = fmaxf(m, s);
+                const float corr = expf(m - mn);              // exp(-inf) = 0 on the first key
+                const float p = expf(s - mn);
+                l = l * corr + p;
+                acc[0] = fmaf(p, va[u].x, acc[0] * corr); acc[1] = fmaf(p, va[u].y, acc[1] * corr);
+                acc[2] = fmaf(p, va[u].z, acc[2] * corr); acc[3] = fmaf(p, va[u].w, acc[3] * corr);
+                acc[4] = fmaf(p, vb[u].x, acc[4] * corr); acc[5] = fmaf(p, vb[u].y, acc[5] * corr);
+                acc[6] = fmaf(p, vb[u].z, acc[6] * corr); acc[7] = fmaf(p, vb[u].w, acc[7] * corr);
+                m = mn;
+            }
+        }
     }
-    mx = warp_max(mx);
-    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
-    __syncthreads();
-    float sum = 0.f;
-    for (int j = tid; j < n; j += 128) {
-        const float e = expf(s_p[j] - mx);
-        s_p[j] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    if ((tid & 31) == 0) s_red[tid >> 5] = sum;
-    __syncthreads();
-    const float inv = 1.0f / (s_red[0] + s_red[1] + s_red[2] + s_red[3]);
-    const int c = tid & 63, half = tid >> 6;
-    float acc = 0.f;
-    for (int j = half; j < n; j += 2) acc = fmaf(s_p[j], vc[(long long)j * d + c], acc);
-    s_o[half][c] = acc;
+    // ---- merge the 16 lane groups ----
+    if (sub == 0) { s_m[w][grp] = m; s_l[w][grp] = l; }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_acc[w][grp][sub * 8 + e] = acc[e];
     __syncthreads();
     if (tid < 64) {
-        const float o = (s_o[0][tid] + s_o[1][tid]) * inv;
+        float M = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) M = fmaxf(M, s_m[i >> 2][i & 3]);
+        float Lsum = 0.f, o = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float mi = s_m[i >> 2][i & 3];
+            const float sc = (mi == -INFINITY) ? 0.f : expf(mi - M);
+            Lsum += s_l[i >> 2][i & 3] * sc;
+            o += s_acc[i >> 2][i & 3][tid] * sc;
+        }
+        o /= Lsum;
         if (out_f32) out_f32[(long long)b * d + h * 64 + tid] = o;
         if (out_hi) {
             __half hi, lo;
@@ -89,14 +112,19 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cross-attention of one new token per sequence over the per-window K and V, both split fp16 and head-major
-// [B][H][T][64]: every (sequence, head) is two contiguous 192 KB streams per plane.  HBM-bound:
-// 2 x 1500 x 64 x (2+2) B = 768 KB per (sequence, head) per step.
+// cross-attention of one new token per sequence over the per-window K and V, head-major [B][H][T][64]: every
+// (sequence, head) is a set of contiguous streams.  HBM-bound, so the decode layout spends 3 bytes per element instead
+// of the 4 of the split-fp16 planes the GEMMs use:
+//     x ~= hi + q * s_row,   hi = fp16(x) (the GEMM plane itself), q = int8 residual (stored biased, u8 = q + 128),
+//     s_row = 2^(E-18) with E the exponent of the largest |hi| of the 64-element row (one float per key row)
+// |x - (hi + q s_row)| <= 2^-19 max|row|: 250x tighter than fp16 alone, ~8x looser than the hi+lo planes -- well inside
+// the parity gates (logits 1e-3; measured in tests/test_gpu_decode.py) -- for 2 x 1500 x (64 x 3 + 4) B = 588 KB per
+// (sequence, head) per step instead of 768 KB.  Single-plane precision (no lo planes) keeps plain fp16 K / V.
 //
 // Flash-decoding layout: the keys of one (b,h) are cut into XS splits; one CTA (4 warps) streams its split ONCE,
-// reading K and V rows of the same key together (8 lanes per 128-byte row, 4 keys per warp load, 16 independent
-// 16-byte loads in flight per lane), with an online softmax per lane group.  Each CTA writes (m, l, acc[64]); the
-// last CTA of a (b,h) to finish (atomic ticket) merges the XS partials and writes the output.
+// reading K and V rows of the same key together (8 lanes per row, 4 keys per warp load, 4 keys in flight per lane
+// group), with an online softmax per lane group.  Each CTA writes (m, l, acc[64]); the last CTA of a (b,h) to finish
+// (atomic ticket) merges the XS partials and writes the output.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int XS = 4;                       // key splits per (sequence, head)
 constexpr int XS_KEYS = 376;                // keys per split (multiple of 8; 4 x 376 >= 1500)
@@ -111,11 +139,22 @@ __device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
     }
 }
 
+// u8 residuals (biased by 128) of 8 elements -> floats: 0x4B000000 | u is the float 8388608 + u
+__device__ __forceinline__ void unpack8q(const uint2& a, float (&f)[8]) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const uint32_t w = e < 4 ? a.x : a.y;
+        f[e] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)(e & 3))) - 8388736.0f;
+    }
+}
+
+template <bool Q8>
 __global__ void __launch_bounds__(128, 3)
-decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const __half* __restrict__ k_lo,
-                         const __half* __restrict__ v_hi, const __half* __restrict__ v_lo, int d, int T,
-                         float* __restrict__ partial, int* __restrict__ tickets, __half* __restrict__ out_hi,
-                         __half* __restrict__ out_lo, float* __restrict__ out_f32) {
+decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const uint8_t* __restrict__ k_q,
+                         const float* __restrict__ k_s, const __half* __restrict__ v_hi, const uint8_t* __restrict__ v_q,
+                         const float* __restrict__ v_s, int d, int T, float* __restrict__ partial,
+                         int* __restrict__ tickets, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
+                         float* __restrict__ out_f32) {
     __shared__ float s_m[4][4], s_l[4][4];
     __shared__ float s_acc[4][4][64];
     __shared__ int s_last;
@@ -128,24 +167,31 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
     float qr[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e] * 0.125f;
-    const long long base = ((long long)b * H + h) * T * 64 + sub * 8;
+    const long long rowbase = ((long long)b * H + h) * T;
+    const long long base = rowbase * 64 + sub * 8;
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     // this lane group's keys: key0 + w*4 + grp + 16*i
     for (int j0 = key0 + w * 4 + grp; j0 < key1 + 48; j0 += 64) {          // warp-uniform trip count
-        uint4 kh[4], kl[4], vh[4], vl[4];
+        uint4 kh[4], vh[4];
+        uint2 kq[4], vq[4];
+        float ks[4], vs[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u * 16;
-            kh[u] = kl[u] = vh[u] = vl[u] = make_uint4(0, 0, 0, 0);
+            kh[u] = vh[u] = make_uint4(0, 0, 0, 0);
+            kq[u] = vq[u] = make_uint2(0x80808080u, 0x80808080u);
+            ks[u] = vs[u] = 0.f;
             if (j < key1) {
                 const long long off = base + (long long)j * 64;
                 kh[u] = __ldg(reinterpret_cast<const uint4*>(k_hi + off));
                 vh[u] = __ldg(reinterpret_cast<const uint4*>(v_hi + off));
-                if (k_lo) {
-                    kl[u] = __ldg(reinterpret_cast<const uint4*>(k_lo + off));
-                    vl[u] = __ldg(reinterpret_cast<const uint4*>(v_lo + off));
+                if (Q8) {
+                    kq[u] = __ldg(reinterpret_cast<const uint2*>(k_q + off));
+                    vq[u] = __ldg(reinterpret_cast<const uint2*>(v_q + off));
+                    ks[u] = __ldg(k_s + rowbase + j);
+                    vs[u] = __ldg(v_s + rowbase + j);
                 }
             }
         }
@@ -154,14 +200,16 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
             const int j = j0 + u * 16;
             float kf[8], t[8];
             unpack8(kh[u], kf);
-            if (k_lo) {
-                unpack8(kl[u], t);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) kf[e] += t[e];
-            }
             float s = 0.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) s = fmaf(qr[e], kf[e], s);
+            if (Q8) {                                         // q . (hi + r s_row) = q . hi + s_row (q . r)
+                unpack8q(kq[u], t);
+                float sr = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) sr = fmaf(qr[e], t[e], sr);
+                s = fmaf(sr, ks[u], s);
+            }
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -171,14 +219,16 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
                 const float p = expf(s - mn);
                 float vf[8];
                 unpack8(vh[u], vf);
-                if (v_lo) {
-                    unpack8(vl[u], t);
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) vf[e] += t[e];
-                }
                 l = l * corr + p;
+                if (Q8) {                                     // acc += p hi + (p s_row) r
+                    unpack8q(vq[u], t);
+                    const float p2 = p * vs[u];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e] * corr);
+                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], fmaf(p2, t[e], acc[e] * corr));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e] * corr);
+                }
                 m = mn;
             }
         }
@@ -238,21 +288,66 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
     }
 }
 
-// V^T split [B][H][64][Tp] -> V split head-major [B][H][T][64] (decode-step layout).  32x32 smem tile transpose.
-__global__ void __launch_bounds__(256) v_headmajor_kernel(const __half* __restrict__ vT, int T, int Tp, __half* __restrict__ v) {
-    __shared__ __half tile[64][72];
+// int8 residual of a 64-element row held two elements per lane: hi = fp16 plane values, lo = fp16 residual plane values.
+// Returns the biased bytes (q + 128) of this lane's two elements and the row scale s_row = 2^(E - 18).
+__device__ __forceinline__ void q8_row(float hi0, float hi1, float lo0, float lo1, uint8_t& u0, uint8_t& u1, float& scale) {
+    uint32_t eb = max(__float_as_uint(hi0) & 0x7f800000u, __float_as_uint(hi1) & 0x7f800000u);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) eb = max(eb, __shfl_xor_sync(0xffffffffu, eb, o));
+    eb = max(eb, 113u << 23);                                // fp16 subnormal rows: E = -14
+    scale = __uint_as_float(eb - (18u << 23));               // 2^(E - 18); |lo| <= 2^(E - 11) -> |q| <= 128
+    const float inv = __uint_as_float((254u << 23) - (eb - (18u << 23)));   // 1 / scale, exact (power of two)
+    const int q0 = max(-127, min(127, __float2int_rn(lo0 * inv)));
+    const int q1 = max(-127, min(127, __float2int_rn(lo1 * inv)));
+    u0 = (uint8_t)(q0 + 128);
+    u1 = (uint8_t)(q1 + 128);
+}
+
+// K head-major split planes [rows][64] -> int8 residual plane + row scales (one warp per row).
+__global__ void __launch_bounds__(256) pack_q8_rows_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
+                                                           long long rows, uint8_t* __restrict__ q, float* __restrict__ scale) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const float2 h = __half22float2(reinterpret_cast<const __half2*>(hi + row * 64)[lane]);
+    const float2 l = __half22float2(reinterpret_cast<const __half2*>(lo + row * 64)[lane]);
+    uint8_t u0, u1;
+    float sc;
+    q8_row(h.x, h.y, l.x, l.y, u0, u1, sc);
+    reinterpret_cast<uint16_t*>(q + row * 64)[lane] = (uint16_t)u0 | ((uint16_t)u1 << 8);
+    if (lane == 0) scale[row] = sc;
+}
+
+// V^T split [B][H][64][Tp] -> V head-major [B][H][T][64] (decode-step layout): fp16 hi plane, and -- when the lo plane
+// is given -- its int8 residual plane + row scales.  64 x 64 smem tile transpose.
+__global__ void __launch_bounds__(256) v_headmajor_kernel(const __half* __restrict__ vT_hi, const __half* __restrict__ vT_lo,
+                                                          int T, int Tp, __half* __restrict__ v_hi, uint8_t* __restrict__ v_q,
+                                                          float* __restrict__ v_s) {
+    __shared__ __half tile[2][64][72];
     const long long bh = blockIdx.y;
     const int t0 = blockIdx.x * 64;
-    const __half* src = vT + bh * 64 * Tp;
+    const bool q8 = vT_lo != nullptr;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
         const int c = i >> 6, t = i & 63;
-        tile[c][t] = (t0 + t < T) ? src[(long long)c * Tp + t0 + t] : __float2half(0.f);
+        const bool ok = t0 + t < T;
+        tile[0][c][t] = ok ? vT_hi[(bh * 64 + c) * Tp + t0 + t] : __float2half(0.f);
+        if (q8) tile[1][c][t] = ok ? vT_lo[(bh * 64 + c) * Tp + t0 + t] : __float2half(0.f);
     }
     __syncthreads();
-    __half* dst = v + bh * T * 64;
-    for (int i = threadIdx.x; i < 64 * 64; i += 256) {
-        const int t = i >> 6, c = i & 63;
-        if (t0 + t < T) dst[(long long)(t0 + t) * 64 + c] = tile[c][t];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = w; t < 64; t += 8) {                        // one warp per key row, two channels per lane
+        if (t0 + t >= T) break;
+        const long long row = bh * T + t0 + t;
+        const __half h0 = tile[0][2 * lane][t], h1 = tile[0][2 * lane + 1][t];
+        reinterpret_cast<__half2*>(v_hi + row * 64)[lane] = __halves2half2(h0, h1);
+        if (q8) {
+            uint8_t u0, u1;
+            float sc;
+            q8_row(__half2float(h0), __half2float(h1), __half2float(tile[1][2 * lane][t]), __half2float(tile[1][2 * lane + 1][t]),
+                   u0, u1, sc);
+            reinterpret_cast<uint16_t*>(v_q + row * 64)[lane] = (uint16_t)u0 | ((uint16_t)u1 << 8);
+            if (lane == 0) v_s[row] = sc;
+        }
     }
 }
 
@@ -431,18 +526,30 @@ int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d
     STB_LAUNCH_OK();
     return STB_OK;
 }
-int decode_attn_cross(const float* q, const __half* kh, const __half* kl, const __half* vh, const __half* vl, int B, int H,
-                      int d, float* partial, int* tickets, __half* oh, __half* ol, float* of, cudaStream_t st) {
-    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0 * (kl ? 2 : 1));
-    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel, dim3(XS, H, B), dim3(128), 0, st, q, kh, kl, vh, vl, d, (int)STB_N_AUDIO_CTX,
-                           partial, tickets, oh, ol, of));
+int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
+                      __half* ol, float* of, cudaStream_t st) {
+    const bool q8 = kv.k_q != nullptr;
+    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * (q8 ? 64 * 3.0 + 4.0 : 64 * 2.0));
+    if (q8)
+        STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<true>, dim3(XS, H, B), dim3(128), 0, st, q, kv.k_hi, kv.k_q, kv.k_s,
+                               kv.v_hi, kv.v_q, kv.v_s, d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
+    else
+        STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<false>, dim3(XS, H, B), dim3(128), 0, st, q, kv.k_hi, kv.k_q, kv.k_s,
+                               kv.v_hi, kv.v_q, kv.v_s, d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
     STB_LAUNCH_OK();
     return STB_OK;
 }
 size_t decode_cross_scratch_bytes(int B, int H) { return (size_t)B * H * XS * 66 * sizeof(float) + (size_t)B * H * sizeof(int) + 256; }
-int v_headmajor(const __half* vT, int BH, int T, int Tp, __half* v, cudaStream_t st) {
-    ProfScope ps("v_headmajor", st, (double)BH * T * 64 * 4.0);
-    v_headmajor_kernel<<<dim3(cdiv(T, 64), BH), 256, 0, st>>>(vT, T, Tp, v);
+int v_headmajor(const __half* vT_hi, const __half* vT_lo, int BH, int T, int Tp, __half* v_hi, uint8_t* v_q, float* v_s,
+                cudaStream_t st) {
+    ProfScope ps("v_headmajor", st, (double)BH * T * 64 * (vT_lo ? 4.0 + 3.0 : 4.0));
+    v_headmajor_kernel<<<dim3(cdiv(T, 64), BH), 256, 0, st>>>(vT_hi, vT_lo, T, Tp, v_hi, v_q, v_s);
+    STB_LAUNCH_OK();
+    return STB_OK;
+}
+int pack_q8_rows(const __half* hi, const __half* lo, long long rows, uint8_t* q, float* scale, cudaStream_t st) {
+    ProfScope ps("pack_q8_rows", st, (double)rows * 64 * 5.0);
+    pack_q8_rows_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(hi, lo, rows, q, scale);
     STB_LAUNCH_OK();
     return STB_OK;
 }

@@ -233,15 +233,20 @@ static int encoder_forward(stb_model* m, const float* mel, int B, float* xa_f32,
 // ---------------------------------------------------------------------------------------------------------
 struct CrossKV {             // per layer: K split head-major [B][H][T][64], vT split [B][H][64][Tp], V split head-major
     size_t k_elems, v_elems, layer_halfs;
+    size_t rows;              // B * H * T key rows (one scale each in the decode-step format)
 };
 static CrossKV cross_layout(const stb_model* m, int B) {
     CrossKV c;
     c.k_elems = (size_t)B * m->dims.n_audio_ctx * m->dims.n_text_state;
     c.v_elems = (size_t)B * m->dims.n_text_state * STB_KPAD;
-    c.layer_halfs = 2 * (2 * c.k_elems + c.v_elems);         // hi + lo planes of K, V^T and the head-major V copy
+    // per layer: K hi | K lo | V^T hi | V^T lo | decode-step region of 2 * k_elems halfs + 4 * rows halfs:
+    //   V head-major hi (k_elems halfs) | K residual u8 (k_elems bytes) | V residual u8 (k_elems bytes) |
+    //   K row scales (rows floats) | V row scales (rows floats),      rows = B * H * T  (decode.cu, 3-byte format)
+    c.rows = (size_t)B * m->dims.n_text_head * m->dims.n_audio_ctx;
+    c.layer_halfs = 2 * (2 * c.k_elems + c.v_elems) + 4 * c.rows;
     return c;
 }
-static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split& K, Split& vT, Split* Vd = nullptr) {
+static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split& K, Split& vT, CrossDecodeKV* Vd = nullptr) {
     CrossKV c = cross_layout(m, B);
     __half* p = (__half*)base + (size_t)l * c.layer_halfs;
     const bool lo = m->prec == STB_PREC_FP16X3;
@@ -249,7 +254,14 @@ static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split
     vT.hi = p + 2 * c.k_elems; vT.lo = lo ? p + 2 * c.k_elems + c.v_elems : nullptr;
     if (Vd) {
         __half* v = p + 2 * c.k_elems + 2 * c.v_elems;
-        Vd->hi = v; Vd->lo = lo ? v + c.k_elems : nullptr;
+        uint8_t* q = reinterpret_cast<uint8_t*>(v + c.k_elems);
+        float* sc = reinterpret_cast<float*>(q + 2 * c.k_elems);
+        Vd->k_hi = K.hi;
+        Vd->v_hi = v;
+        Vd->k_q = lo ? q : nullptr;
+        Vd->v_q = lo ? q + c.k_elems : nullptr;
+        Vd->k_s = lo ? sc : nullptr;
+        Vd->v_s = lo ? sc + c.rows : nullptr;
     }
 }
 
@@ -260,7 +272,8 @@ static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int 
     Split xa = {(__half*)xa_hi, m->prec == STB_PREC_FP16X3 ? (__half*)xa_lo : nullptr};
     for (int l = 0; l < D.n_text_layer; ++l) {
         const stb_model::Layer& L = m->dec[l];
-        Split K, vT, Vd;
+        Split K, vT;
+        CrossDecodeKV Vd;
         cross_ptrs(m, B, out, l, K, vT, &Vd);
         {   // K head-major [B][H][T][64] (sequential 192 KB streams per (sequence, head) for the decode-step kernel):
             // per-head batched GEMM, A = xa broadcast over heads, B = rows h*64..h*64+63 of W_k; whisper's key has no bias
@@ -273,8 +286,11 @@ static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int 
         STB_TRY(project_vT(m, xa, B, T, d, offs(W_HI(L, STB_L_CKV_W), (long long)d * d), offs(W_LO(L, STB_L_CKV_W), (long long)d * d),
                            W_F32(L, STB_L_CKV_B) + d, vT, STB_KPAD, st));
         if (decode_layout) {   // head-major copy of V for the decode-step kernel (contiguous per (sequence, head), like K)
-            STB_TRY(v_headmajor(vT.hi, B * D.n_text_head, T, STB_KPAD, Vd.hi, st));
-            if (Vd.lo) STB_TRY(v_headmajor(vT.lo, B * D.n_text_head, T, STB_KPAD, Vd.lo, st));
+            STB_TRY(v_headmajor(vT.hi, vT.lo, B * D.n_text_head, T, STB_KPAD, const_cast<__half*>(Vd.v_hi),
+                                const_cast<uint8_t*>(Vd.v_q), const_cast<float*>(Vd.v_s), st));
+            if (K.lo)   // 3-byte decode format of K: int8 residual + row scale next to the fp16 hi plane
+                STB_TRY(pack_q8_rows(K.hi, K.lo, (long long)B * D.n_text_head * T, const_cast<uint8_t*>(Vd.k_q),
+                                     const_cast<float*>(Vd.k_s), st));
         }
     }
     return STB_OK;
@@ -515,9 +531,10 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
                     none, d, W_F32(L, STB_L_CROSS_LN_G), W_F32(L, STB_L_CROSS_LN_B)));
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_CQ_W), W_LO(L, STB_L_CQ_W), d, W_F32(L, STB_L_CQ_B), STB_ACT_NONE, nullptr, w.q,
                     none, d, nullptr, nullptr));
-        Split Kx, vTx, Vd;
+        Split Kx, vTx;
+        CrossDecodeKV Vd;
         cross_ptrs(m, B, ckv, l, Kx, vTx, &Vd);
-        STB_TRY(decode_attn_cross(w.q, Kx.hi, Kx.lo, Vd.hi, Vd.lo, B, H, d, w.xpart, w.tickets, w.attn.hi, w.attn.lo, nullptr, st));
+        STB_TRY(decode_attn_cross(w.q, Vd, B, H, d, w.xpart, w.tickets, w.attn.hi, w.attn.lo, nullptr, st));
         STB_TRY(lin(w.attn, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d, W_F32(L, STB_L_COUT_B), STB_ACT_NONE, w.x,
                     w.x, none, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B)));
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_FC1_W), W_LO(L, STB_L_FC1_W), 4 * d, W_F32(L, STB_L_FC1_B), STB_ACT_GELU, nullptr,

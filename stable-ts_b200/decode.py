@@ -68,12 +68,17 @@ def _suppress_list(tokenizer, options: DecodingOptions) -> List[int]:
 class StepEngine:
     """Device state of a batch of B decoding sequences + the two launch sequences of one step."""
 
-    def __init__(self, model: B200Whisper, B: int, table_rows: int):
+    def __init__(self, model: B200Whisper, B: int, table_rows: int, reuse_buffers: bool = False):
         self.m, self.B, self.rows = model, B, table_rows
         dev, lib, V = model.device, model._lib, model.dims.n_vocab
         self.ldv = (V + 7) // 8 * 8
-        self.state = torch.zeros(lib.stb_decode_state_bytes(model._h, B), dtype=torch.uint8, device=dev)
-        self.ws = torch.zeros(lib.stb_decode_ws_bytes(model._h, B), dtype=torch.uint8, device=dev)   # tickets start at 0
+        if reuse_buffers:      # model-owned: the self-attention K/V cache (rows beyond `pos` are never read) and the workspace
+            self.state = model._buf("decode_state", lib.stb_decode_state_bytes(model._h, B))
+            self.ws = model._buf("decode_ws", lib.stb_decode_ws_bytes(model._h, B))
+            self.ws.zero_()                                                                          # tickets start at 0
+        else:
+            self.state = torch.zeros(lib.stb_decode_state_bytes(model._h, B), dtype=torch.uint8, device=dev)
+            self.ws = torch.zeros(lib.stb_decode_ws_bytes(model._h, B), dtype=torch.uint8, device=dev)   # tickets start at 0
         self.pos = torch.zeros(1, dtype=torch.int32, device=dev)
         self.logits = torch.empty(B, self.ldv, dtype=torch.float32, device=dev)
         self.seq = torch.zeros(B, 6, dtype=torch.int32, device=dev)          # stb_seq_state[B]
@@ -106,12 +111,15 @@ class StepEngine:
 @torch.no_grad()
 def decode_windows(model: B200Whisper, tokenizer, enc: dict, options: Optional[DecodingOptions] = None, *,
                    ts_token_mask: Optional[torch.Tensor] = None, forced_tokens: Optional[torch.Tensor] = None,
-                   use_graph: bool = True, poll_every: int = 16, return_step_logits: bool = False, ckv=None):
+                   use_graph: bool = True, poll_every: int = 16, return_step_logits: bool = False, ckv=None,
+                   reuse_buffers: bool = False):
     """Greedy (temperature 0) decode of the B windows whose encoder output is ``enc`` (from ``model.encode``).
 
     ts_token_mask: bool [1501] shared by the batch (silent-timestamp suppression, decode.py:14-16) or None.
     forced_tokens: int [steps, B] -- the token appended at each step instead of the argmax (fixed-length scripts for
                    random-weight benchmarks); the argmax of every step is still returned.
+    reuse_buffers: keep the cross K/V block, the KV cache and the step workspace in model-owned buffers (the returned
+                   ``extras["ckv"]`` is then only valid until the next such call).
     -> (list of DecodingResult, extras dict(step_argmax [steps,B], step_tokens, sum_logprob, ckv))
     """
     options = options or DecodingOptions()
@@ -125,10 +133,10 @@ def decode_windows(model: B200Whisper, tokenizer, enc: dict, options: Optional[D
     init = list(tokenizer.sot_sequence_including_notimestamps if options.without_timestamps else tokenizer.sot_sequence)
     sample_begin = len(init)
     steps = sample_len if forced_tokens is None else min(sample_len, int(forced_tokens.shape[0]))
-    eng = StepEngine(model, B, steps)
+    eng = StepEngine(model, B, steps, reuse_buffers=reuse_buffers)
     eng.reset()
     if ckv is None:
-        ckv = model.cross_kv(enc, decode=True)
+        ckv = model.cross_kv(enc, decode=True, reuse=reuse_buffers)
     # filter tables (SuppressTokens, SuppressBlank)
     sup = torch.zeros(V, dtype=torch.uint8)
     sup[_suppress_list(tokenizer, options)] = 1 if options.suppress_tokens else 0

@@ -236,10 +236,13 @@ class B200Whisper:
                                               L.stream_ptr()))
         return {"f32": xa, "hi": hi, "lo": lo, "B": B}
 
-    def cross_kv(self, enc: Dict[str, torch.Tensor], decode: bool = False) -> torch.Tensor:
-        """Cross-attention K / V^T of every decoder layer; ``decode=True`` also lays V out for the KV-cached decode step."""
+    def cross_kv(self, enc: Dict[str, torch.Tensor], decode: bool = False, reuse: bool = False) -> torch.Tensor:
+        """Cross-attention K / V^T of every decoder layer; ``decode=True`` also lays V out for the KV-cached decode step.
+        ``reuse=True`` writes into a buffer owned by the model (overwritten by the next such call): a batch of 120
+        large-v3 windows is an 82 GB block, and returning it to the caching allocator every step costs ~1 s."""
         B = enc["B"]
-        out = torch.empty(self._lib.stb_cross_kv_bytes(self._h, B), dtype=torch.uint8, device=self.device)
+        nbytes = self._lib.stb_cross_kv_bytes(self._h, B)
+        out = self._buf("cross_kv", nbytes) if reuse else torch.empty(nbytes, dtype=torch.uint8, device=self.device)
         L.check(self._lib.stb_cross_kv(self._h, L.ptr(enc["hi"]), L.ptr(enc["lo"]), B, int(decode), L.ptr(out), L.stream_ptr()))
         return out
 

@@ -122,12 +122,21 @@ class Tokenizer:
     def encode(self, text: str, **kw) -> List[int]:
         return self.codec.encode(text)
 
+    _piece_cache = None     # id -> bytes, per instance (the host bookkeeping decodes every token several times per window)
+
     def _decode_all(self, ids) -> str:
-        buf = b""
+        cache = self._piece_cache
+        if cache is None:
+            cache = self._piece_cache = {}
+        out = []
         for t in ids:
-            t = int(t)
-            buf += self.codec.piece(t) if t < self.codec.n_base else self._special_by_id[t].encode()
-        return buf.decode("utf-8", errors="replace")
+            b = cache.get(t)
+            if b is None:
+                t = int(t)
+                b = self.codec.piece(t) if t < self.codec.n_base else self._special_by_id[t].encode()
+                cache[t] = b
+            out.append(b)
+        return b"".join(out).decode("utf-8", errors="replace")
 
     def decode(self, ids, **kw) -> str:
         return self._decode_all([t for t in ids if int(t) < self.timestamp_begin])

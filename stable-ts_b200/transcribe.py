@@ -91,8 +91,10 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
     offs = list(time_offsets) if time_offsets is not None else [0.0] * B
     if options is None:                      # transcribe_stable defaults max_initial_timestamp to None (original_whisper.py:262-263)
         options = DecodingOptions(max_initial_timestamp=None)
+    # the cross K/V block and the KV cache live in model-owned buffers: they are consumed inside this call (decode loop, then
+    # the alignment pass below) and are by far the largest allocations of a step
     results, extras = decode_windows(model, tokenizer, enc, options, ts_token_mask=ts_token_mask,
-                                     forced_tokens=forced_tokens, use_graph=use_graph)
+                                     forced_tokens=forced_tokens, use_graph=use_graph, reuse_buffers=True)
     windows = []
     for b in range(B):
         dur = n_samples[b] / SAMPLE_RATE
