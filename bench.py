@@ -299,15 +299,18 @@ def run_b200(args, dims_tuple):
         return
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = lib.stb_launch_count()
+    l0 = lib.stb_launch_count() + model.graph_kernel_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     e0.record()
     for i in range(args.steps):
         device_step(i % pools)
+        marks[i].record()
     e1.record()
     barrier()
-    launches = (lib.stb_launch_count() - l0) // max(args.steps, 1)
+    launches = (lib.stb_launch_count() + model.graph_kernel_launches - l0) // max(args.steps, 1)   # eager + graph replays
     ms = e0.elapsed_time(e1)
+    step_ms = [round(a.elapsed_time(b), 1) for a, b in zip([e0] + marks[:-1], marks)]    # per-step spread (rank 0)
     clocks = sampler.stop()
     t = torch.tensor([ms], device=dev)
     if world > 1:
@@ -330,8 +333,11 @@ def run_b200(args, dims_tuple):
     n_words_total = sum(len(w) for w in merged)          # words actually aligned per step over all ranks
     barrier()
     t0 = time.perf_counter()
+    e2e_step_ms = []
     for i in range(args.steps):
+        t1 = time.perf_counter()
         e2e_step(i % pools)
+        e2e_step_ms.append(round((time.perf_counter() - t1) * 1e3, 1))
     barrier()
     e2e_s = (time.perf_counter() - t0) / args.steps
     t = torch.tensor([e2e_s], device=dev)
@@ -368,6 +374,34 @@ def run_b200(args, dims_tuple):
             "gemm_share_of_step": g_ms.value / ms_step if ms_step > 0 else None,
             "algorithmic_gflop_per_window": algorithmic_flops_per_window(model.dims, args.tokens, S) / 1e9}
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # The decode-step cross-attention is the other heavy kernel (HBM-bound: it streams every window's cross K/V once per
+    # step).  Whichever of the two takes more of the step is reported as "roofline", the other as "roofline_other".
+    roof_x = None
+    try:
+        xp = prof.get("decode_cross_attn")
+        if xp and xp["ms"] > 0 and xp["n"] > 0:
+            x_gbs = xp["bytes"] / (xp["ms"] * 1e-3) / 1e9
+            H = model.dims.n_text_head
+            # ncu --set full at 120 windows (profiles/r1_summary_c.md): dram read + write = 1418.7 MB per launch = 591.1 KB
+            # per (sequence, head); algorithmic 2 x 1500 x (64 x 3 + 4) B = 588 KB -- parity mode, head_dim 64 (any width)
+            traffic = 591.1e3 * Wn * H if args.precision == "fp16x3" else None
+            roof_x = {"bound": "hbm", "kernel": "decode_cross_attn_kernel (flash-decoding over the per-window cross K/V)",
+                      "achieved": x_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": x_gbs / hbm_peak,
+                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                      "traffic": traffic, "algorithmic_bytes_per_launch": xp["bytes"] / xp["n"],
+                      "avg_launch_us": xp["ms"] * 1e3 / xp["n"], "launches_per_step": int(xp["n"]), "ms_per_step": xp["ms"],
+                      "share_of_step": xp["ms"] / ms_step if ms_step > 0 else None,
+                      "note": "achieved = algorithmic bytes per launch (B x H x 2 x 1500 x (64 x 3 + 4) B: fp16 + int8 residual + row "
+                              "scale) / event-timed average launch duration"}
+    except Exception as e:                                  # diagnostics must never cost the bench line
+        print(f"[bench] cross-attention roofline skipped: {e}", file=sys.stderr)
+        roof_x = None
+    roof_other = None
+    if roof_x is not None:
+        if roof_x["ms_per_step"] > g_ms.value:
+            roof, roof_other = roof_x, roof
+        else:
+            roof_other = roof_x
     kernels = {k: {"launches": v["n"], "ms": round(v["ms"], 3),
                    "GBps": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 and v["bytes"] > 0 else None,
                    "hbm_frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak, 3) if v["ms"] > 0 and v["bytes"] > 0 else None}
@@ -388,6 +422,7 @@ def run_b200(args, dims_tuple):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 x3 split (fp32-grade), fp32 accumulate" if args.precision == "fp16x3" else "f16, fp32 accumulate",
         "data": "synthetic", "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
+        "step_ms": step_ms, "e2e_step_ms": e2e_step_ms,
         "allocator": {k: int(torch.cuda.memory_stats().get(k, 0)) for k in ("num_alloc_retries", "num_ooms", "num_device_alloc",
                                                                                "num_device_free")},
         "config": {"workload": (f"transcribe+word_timestamps {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} forced "
@@ -398,7 +433,8 @@ def run_b200(args, dims_tuple):
                    "alignment_heads": args.alignment_heads,
                    "l2": "per-step working set (weights 6.2 GB + activations) >> 126 MB L2; inputs rotate between 2 pools"},
         "rtf": 1.0 / value, "aligned_words_per_s": n_words_total / (ms_step / 1e3),
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_other": roof_other, "kernels": kernels,
+        "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "audio_s/s", "h2d_bytes_per_step": Wn * N_SAMPLES * 4,
                 # jumps int32 [N+1] + token probs fp32 [N] per window (+ token/argmax tables and sampler state for decode)
                 "d2h_bytes_per_step": int(Wn * ((args.tokens + 3) * 4 + (args.tokens + 2) * 4)

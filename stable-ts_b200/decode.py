@@ -87,6 +87,7 @@ class StepEngine:
         self.arg_table = torch.zeros(table_rows, B, dtype=torch.int32, device=dev)
         self.forced = None
         self.graph = None
+        self.graph_nodes = 0          # kernels in the captured step graph
 
     def reset(self):
         self.pos.zero_()
@@ -178,10 +179,14 @@ def decode_windows(model: B200Whisper, tokenizer, enc: dict, options: Optional[D
             if eng.graph is None:
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
+                c0 = model._lib.stb_launch_count()
                 with torch.cuda.graph(g):
                     one_step()                          # this capture pass does not execute; replay below does
                 eng.graph = g
+                eng.graph_nodes = int(model._lib.stb_launch_count() - c0)
+                model.graph_kernel_launches -= eng.graph_nodes      # counted by the library at capture, but not executed
             eng.graph.replay()
+            model.graph_kernel_launches += eng.graph_nodes          # kernels executed by this replay
         else:
             one_step()
         done_steps += 1

@@ -77,6 +77,7 @@ class B200Whisper:
         self._want_lo = self._prec == L.STB_PREC_FP16X3
         self._keep: List[torch.Tensor] = []
         self._ws: Dict[str, torch.Tensor] = {}
+        self.graph_kernel_launches = 0     # kernels executed by CUDA-graph replays (the library counter only sees captures)
         self._lib = L.lib()
         d = L.Dims(**self.dims.__dict__)
         h = ctypes.c_void_p()
@@ -248,13 +249,21 @@ class B200Whisper:
 
     # ---- a3 ----
     def decode_forced(self, tokens: torch.Tensor, ckv: torch.Tensor, want_logits: bool = True,
-                      heads: Union[None, str, Sequence[Tuple[int, int]]] = None):
-        """tokens int [B, M] -> (logits fp32 [B, M, V] view or None, qk fp32 [B, n_sel, M, 1504] or None)."""
+                      heads: Union[None, str, Sequence[Tuple[int, int]]] = None, reuse: bool = False):
+        """tokens int [B, M] -> (logits fp32 [B, M, V] view or None, qk fp32 [B, n_sel, M, 1504] or None).
+        ``reuse=True``: both outputs live in model-owned buffers (valid until the next such call)."""
         tokens = tokens.to(self.device, torch.int32).contiguous()
         B, M = tokens.shape
         V = self.dims.n_vocab
         ldv = (V + 7) // 8 * 8
-        logits = torch.empty(B * M, ldv, dtype=torch.float32, device=self.device) if want_logits else None
+        def out(name, *shape):
+            n = 1
+            for v in shape:
+                n *= v
+            if reuse:
+                return self._buf(name, 4 * n)[: 4 * n].view(torch.float32).view(*shape)
+            return torch.empty(*shape, dtype=torch.float32, device=self.device)
+        logits = out("dec_logits", B * M, ldv) if want_logits else None
         qk, sel, n_sel = None, None, 0
         if heads is not None:
             if isinstance(heads, str):
@@ -265,7 +274,7 @@ class B200Whisper:
                 flat = [int(v) for pair in heads for v in pair]
                 sel = (ctypes.c_int32 * len(flat))(*flat)
                 n_sel = n_tot = len(heads)
-            qk = torch.empty(B, n_tot, M, L.KPAD, dtype=torch.float32, device=self.device)
+            qk = out("dec_qk", B, n_tot, M, L.KPAD)
         ws = self._buf("dec", self._lib.stb_decoder_ws_bytes(self._h, B, M))
         L.check(self._lib.stb_decoder_forward(self._h, L.ptr(tokens), B, M, L.ptr(ckv), L.ptr(logits), ldv, L.ptr(qk), sel,
                                               n_sel, L.ptr(ws), ws.numel(), L.stream_ptr()))

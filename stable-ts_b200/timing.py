@@ -54,7 +54,7 @@ def token_row(tokenizer, text_tokens: Sequence[int]) -> List[int]:
 
 
 def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, enc=None, ckv=None, heads=None,
-                         want_logits: bool = True):
+                         want_logits: bool = True, reuse_buffers: bool = False):
     """Device side of ``_compute_qks`` for a batch of windows.  Returns dict(enc, ckv, logits, qk, M, S, rows)."""
     B = len(jobs)
     if enc is None:
@@ -75,7 +75,7 @@ def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *
         mel = model.log_mel(audio)                         # == log_mel_spectrogram(audio, padding=N_SAMPLES-n)
         enc = model.encode(mel)
     if ckv is None:                                        # cross K/V of the window batch (reused from the decode pass)
-        ckv = model.cross_kv(enc)
+        ckv = model.cross_kv(enc, reuse=reuse_buffers)
     S = len(tokenizer.sot_sequence)
     rows = [token_row(tokenizer, j.text_tokens) for j in jobs]
     M = max(len(r) for r in rows)
@@ -83,7 +83,7 @@ def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *
     for i, r in enumerate(rows):
         tok[i, : len(r)] = torch.tensor(r, dtype=torch.int32)
     logits, qk = model.decode_forced(tok, ckv, want_logits=want_logits,
-                                     heads=model.alignment_head_pairs if heads is None else heads)
+                                     heads=model.alignment_head_pairs if heads is None else heads, reuse=reuse_buffers)
     return dict(enc=enc, ckv=ckv, logits=logits, qk=qk, M=M, S=S, rows=rows)
 
 
@@ -114,7 +114,10 @@ def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfi
     if count is None and not new and getattr(model, "missing_alignment_heads", False):
         count = 6
     all_heads = bool(count) or new
-    fw = window_batch_forward(model, tokenizer, jobs, enc=enc, ckv=ckv, heads="all" if all_heads else None)
+    # logits / QK / cross K/V are consumed inside this function (only host arrays leave it), so they live in model-owned
+    # buffers unless the caller asked for the intermediates
+    fw = window_batch_forward(model, tokenizer, jobs, enc=enc, ckv=ckv, heads="all" if all_heads else None,
+                              reuse_buffers=not return_intermediates)
     S, logits, qk, M = fw["S"], fw["logits"], fw["qk"], fw["M"]
     inter = []
     # windows with the same (N, F) share one post-processing / DTW launch
