@@ -76,3 +76,32 @@ def test_two_rank_gloo_gather_equals_unsharded():
         for a, b in zip(expect, merged):
             assert [w["tokens"] for w in a] == [w["tokens"] for w in b]
             assert np.allclose([w["end"] for w in a], [w["end"] for w in b], atol=1e-9)
+
+
+def test_gathered_words_lazy_view_equals_eager_unpack():
+    """the lazy view over the gathered rank buffers builds exactly the dicts of the eager unpack (empty windows, ragged
+    word counts, negative / slice indexing)"""
+    import numpy as np
+    from stable_ts_b200 import sharding as S
+    rng = np.random.default_rng(3)
+    world, per = 3, 7
+    res = []
+    for w in range(per):
+        ws, t = [], 0.0
+        for _ in range(int(rng.integers(0, 9))):
+            k = int(rng.integers(1, 4))
+            ws.append(dict(word="x", start=round(t, 3), end=round(t + 0.14, 3), probability=float(np.float32(rng.random())),
+                           tokens=[int(v) for v in rng.integers(0, 50000, size=k)]))
+            t += 0.14
+        res.append(ws)
+    res[2] = []
+    cap_w, cap_t = S.capacity(per * world, world)
+    bufs = [S.pack_records(res, per * r, cap_w, cap_t) for r in range(world)]
+    eager = S.unpack_records(bufs, per * world, cap_w)
+    lazy = S.unpack_records(bufs, per * world, cap_w, lazy=True)
+    assert len(lazy) == per * world and lazy.n_words == world * sum(len(w) for w in res)
+    assert [lazy[i] for i in range(len(lazy))] == eager
+    assert lazy[-1] == eager[-1] and lazy[1:4] == eager[1:4]
+    for r in range(world):
+        for w in range(per):
+            assert [d["tokens"] for d in eager[per * r + w]] == [d["tokens"] for d in res[w]]
