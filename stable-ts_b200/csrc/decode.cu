@@ -1,9 +1,10 @@
 // a9 / K10: KV-cached autoregressive decode step (stable_whisper/decode.py:33-65 -> whisper PyTorchInference.logits with
 // kv-cache hooks, the logit filters, GreedyDecoder.update).
 //
-//   stb_decode_step     one decoder forward for the newest token of B sequences: GEMMs on the tcgen05 core (M = B rows,
-//                       narrow N tiles so >=120 CTAs stream the weights), attention over the caches on CUDA cores
-//                       (one query row per (sequence, head): no tensor-core shape), HBM-bound by weights + cross K/V.
+//   stb_decode_step     one decoder forward for the newest token of B sequences (engine.cu: decode_step).  Linear layers:
+//                       mma.sync batched GEMV (gemv.cu) up to 16 sequences, swapped split-K tcgen05 GEMM + fused
+//                       finish/LayerNorm up to 128.  Attention over the caches runs on CUDA cores in this file (one query
+//                       row per (sequence, head): no tensor-core shape), flash-decoding style, HBM-bound by the cross K/V.
 //   stb_sample_greedy   SuppressBlank / SuppressTokens / ApplyTimestampRules / silent-timestamp mask / argmax /
 //                       log-prob accumulation / EOT latching fused into one kernel per step, state kept on the device.
 //
@@ -401,7 +402,6 @@ sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, i
                      int32_t* __restrict__ next_out, int32_t* __restrict__ token_table, int32_t* __restrict__ argmax_table,
                      int table_rows) {
     __shared__ BlockRed red;
-    __shared__ int s_arg;
     const int b = blockIdx.x;
     pdl_trigger();
     pdl_wait();
@@ -475,7 +475,6 @@ sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, i
     if (threadIdx.x == 0) {
         int a = red.i[0];
         for (int k = 1; k < (int)(blockDim.x >> 5); ++k) a = min(a, red.i[k]);
-        s_arg = a;
         const float log_s = logf(s);                          // lse = gmax + log_s; kept apart: gmax may be -FLT_MAX
         const bool was_done = st.n_sampled >= 1 && st.last_tok == eot;
         int next = a;
