@@ -299,3 +299,20 @@ def words_from_script(tokens: Sequence[int], seed: int = 7) -> List[List[int]]:
         out.append(list(tokens[i:i + k]))
         i += k
     return out
+
+
+def synth_gapped_audio(n_samples: int, seed: int = 77, floor: float = 0.0) -> torch.Tensor:
+    """``synth_audio`` with silent / near-silent stretches (random 0.05-2.5 s gaps, ``floor`` = residual noise amplitude in
+    the gaps): exercises the silence detector."""
+    x = synth_audio(n_samples, seed=seed).double()
+    g = torch.Generator().manual_seed(seed + 1000)
+    env = torch.ones(n_samples, dtype=torch.float64)
+    pos = int(torch.randint(0, 16000, (1,), generator=g))
+    while pos < n_samples:
+        gap = int((0.05 + 2.45 * float(torch.rand(1, generator=g))) * 16000)
+        env[pos:pos + gap] = 0.0
+        pos += gap + int((0.2 + 3.0 * float(torch.rand(1, generator=g))) * 16000)
+    y = x * env
+    if floor > 0:
+        y = y + floor * torch.randn(n_samples, generator=g, dtype=torch.float64) * (1 - env)
+    return y.float()
