@@ -222,6 +222,18 @@ STB_API size_t stb_dtw_ws_bytes(int B, int R, int F);   /* transposed + skewed c
 STB_API int stb_dtw(const float* x, int B, int R, int F, long long ldx, int negate, int32_t* jumps, int32_t* path,
             int32_t* path_len, void* ws, size_t ws_bytes, void* stream);
 
+/* Section 8(f) row 1 -- non-VAD silence detection, device part (stable_whisper/stabilization/nonvad.py:16-41 audio2loudness,
+ *    :58-76 of wav2mask: moving average, quantisation, -> bool).  Per window of a batch [B][stride] of 16 kHz fp32 samples:
+ *    threshold = k-th largest |x| (k = int(n * 0.001), computed by the caller), loudness [token_count] = linear
+ *    down-sampling of |x| / min(1, 1.75 threshold) (token_count = round(n / 320) + 1, computed by the caller), mask =
+ *    round(avg_pool(loudness, k_size, reflect) * q_levels) != 0  (1 = sound).  Outputs have a row pitch of 1501.
+ *    thr_in (nullable): per-window thresholds supplied by the caller instead of the k-th largest (the reference's
+ *    quantile branch for windows shorter than 1000 samples).  loudness_out / thr_out may be NULL.
+ *    The run-length logic of wav2mask (:76-88) stays with the caller (stable-ts_b200/silence.py). */
+STB_API int stb_silence_mask(const float* audio, int B, int n_samples, long long stride, int k, int token_count, int q_levels,
+                             int k_size, const float* thr_in, float* loudness_out, uint8_t* mask_out, float* thr_out,
+                             void* stream);
+
 /* a9 KV-cached decode (stable_whisper/decode.py:33-65; whisper PyTorchInference.logits + logit filters +
  *    GreedyDecoder.update).  One step = one decoder forward for the newest token of B sequences.
  *    Everything position-dependent is read from the DEVICE counter `pos` (index of the token being fed), which the step

@@ -50,6 +50,8 @@ _SIGS = {
     "stb_gemm": (c_int, [POINTER(Operand), POINTER(Operand), c_int, c_int, POINTER(Epilogue), c_void_p]),
     "stb_attention": (c_int, [POINTER(Operand), POINTER(Operand), POINTER(Operand), c_int, c_int, c_int, c_int, c_void_p,
                               c_void_p, c_longlong, c_longlong, c_longlong, c_void_p]),
+    "stb_silence_mask": (c_int, [c_void_p, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "stb_gemv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_longlong,
                          c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "stb_split_f16": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p]),

@@ -125,3 +125,40 @@ def test_n_frames_uses_bankers_rounding():
     from stable_ts_b200.timing import n_frames_for
     assert n_frames_for(480000) == 1500 and n_frames_for(160) == 0 and n_frames_for(480) == 2 and n_frames_for(800) == 2
     assert n_frames_for(1120) == 4                      # 3.5 -> 4 (even), 2.5 -> 2 above
+
+
+def test_silence_host_bookkeeping_matches_oracle(monkeypatch):
+    """stable_ts_b200.silence: everything after the kernel (run lengths, 0.1 s filter, suppression mask, predictor dict)
+    equals the oracle / the fixtures written by the reference when it is fed the oracle's sound masks."""
+    import numpy as np
+    import torch
+    from oracle import silence as SIL
+    from oracle.make_golden_silence import CASES, case_audio
+    from stable_ts_b200 import silence as S
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        m = rng.random(int(rng.integers(3, 1502))) < rng.random()
+        for off in (0.0, 7.5):
+            a, b = S.mask2timing(m, time_offset=off), SIL.mask2timing(m, time_offset=off)
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+                assert np.array_equal(S.timing2mask(a[0], a[1], len(m), time_offset=off), SIL.timing2mask(b[0], b[1], len(m), time_offset=off))
+        x, y = S._silence_from_sound(m), SIL.raw_mask_to_silence_mask(m)
+        assert (x is None) == (y is None) and (x is None or np.array_equal(x, y))
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "silence_cases.npz"))
+    for i, (n, seed, floor, scale) in enumerate(CASES):
+        audio = case_audio(int(n), int(seed), floor, scale)
+        loud = SIL.audio2loudness(audio.numpy())
+
+        def fake_sound_masks(a, q_levels=20, k_size=5, want_loudness=False):
+            return (None, None) if loud is None else (SIL.loudness_to_raw_mask(loud, q_levels, k_size)[None], None)
+        monkeypatch.setattr(S, "sound_masks", fake_sound_masks)
+        pred = S.predict_nonvad_batch(audio[None], offsets=[12.5])[0]
+        assert (pred["timings"] is not None) == bool(z[f"has_timings_{i}"])
+        if pred["timings"] is not None:
+            assert np.array_equal(pred["timings"], z[f"timings_{i}"])
+        assert pred["is_silent"] == bool(z[f"silent_{i}"])
+        assert (pred["mask"] is None) == (z[f"pmask_{i}"].size == 0)
+        if pred["mask"] is not None:
+            assert pred["mask"].dtype == torch.bool and np.array_equal(pred["mask"].numpy(), z[f"pmask_{i}"])
