@@ -291,6 +291,36 @@ def run_b200(args, dims_tuple):
     for i in range(args.warmup):
         device_step(i % pools)
     barrier()
+
+    # ---- full-size self-check (size-independent property): the first, middle and last window of the full batch, processed
+    # again as a batch of 3 (different kernels: mma.sync GEMV decode linears instead of the split-K GEMMs, other grid sizes,
+    # other buffer offsets), must give the same words -- catches index overflow / layout faults that only show at 100+ windows
+    selfcheck = None
+    if args.workload == "transcribe" and rank == 0 and not args.ncu:
+        try:
+            idx = sorted({0, Wn // 2, Wn - 1})
+            full, _ = transcribe_windows(model, tk, host_audio[0], options=dopt, forced_tokens=scripts[0])
+            small, _ = transcribe_windows(model, tk, host_audio[0][idx].contiguous(), options=dopt,
+                                          forced_tokens=scripts[0][:, idx].contiguous())
+            worst_t, worst_p, n_cmp, bad = 0.0, 0.0, 0, None
+            for k, i in enumerate(idx):
+                wa = [w for s_ in full[i] for w in s_["words"]]
+                wb = [w for s_ in small[k] for w in s_["words"]]
+                if len(wa) != len(wb) or any(x["tokens"] != y["tokens"] for x, y in zip(wa, wb)):
+                    bad = f"window {i}: word lists differ ({len(wa)} vs {len(wb)} words)"
+                    break
+                for x, y in zip(wa, wb):
+                    worst_t = max(worst_t, abs(x["start"] - y["start"]), abs(x["end"] - y["end"]))
+                    worst_p = max(worst_p, abs(x["probability"] - y["probability"]) / max(abs(y["probability"]), 1e-30))
+                    n_cmp += 1
+            ok = bad is None and worst_t <= 0.0201 and worst_p <= 2e-3
+            selfcheck = {"ok": bool(ok), "windows": idx, "words_compared": n_cmp, "worst_word_dt_s": round(worst_t, 4),
+                         "worst_prob_rel": float(f"{worst_p:.3e}"), "detail": bad}
+            del full, small
+        except Exception as e:                              # a diagnostic: never costs the bench line
+            selfcheck = {"ok": None, "detail": f"self-check did not run: {type(e).__name__}: {e}"}
+        print(f"[bench] self-check: {selfcheck}", file=sys.stderr)
+    barrier()
     if args.ncu:                                        # `ncu --profile-from-start off ... bench.py --ncu`
         torch.cuda.profiler.start()
         device_step(0)
@@ -424,7 +454,7 @@ def run_b200(args, dims_tuple):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 x3 split (fp32-grade), fp32 accumulate" if args.precision == "fp16x3" else "f16, fp32 accumulate",
         "data": "synthetic", "peak_hbm_gb": round(torch.cuda.max_memory_allocated() / 2 ** 30, 1),
-        "step_ms": step_ms, "e2e_step_ms": e2e_step_ms,
+        "step_ms": step_ms, "e2e_step_ms": e2e_step_ms, "selfcheck": selfcheck,
         "allocator": {k: int(torch.cuda.memory_stats().get(k, 0)) for k in ("num_alloc_retries", "num_ooms", "num_device_alloc",
                                                                                "num_device_free")},
         "config": {"workload": (f"transcribe+word_timestamps {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} forced "
