@@ -149,7 +149,17 @@ __device__ __forceinline__ void unpack8q(const uint2& a, float (&f)[8]) {
     }
 }
 
-template <bool Q8>
+// biased u8 residuals of elements (k, k+1) of one 32-bit word -> half2 (r_k, r_k+1), exact: 0x6400 | u is the half 1024 + u
+__device__ __forceinline__ __half2 q8_pair(uint32_t w, int k) {
+    const uint32_t sel = k == 0 ? 0x4140u : 0x4342u;          // bytes [u_k, 0x64, u_k+1, 0x64]
+    const uint32_t bits = __byte_perm(w, 0x64646464u, sel);
+    return __hsub2(*reinterpret_cast<const __half2*>(&bits), __floats2half2_rn(1152.f, 1152.f));
+}
+
+// V2 (STB_XATTN_V2=1, not the default until it has run on hardware): (a) the residual part of q.k is a correction of
+// relative size <= 2^-11, so it is evaluated with packed half2 FMAs (its own 2^-11 rounding lands at 2^-22 of the score);
+// (b) the online-softmax rescale happens once per block of 4 keys instead of once per key.
+template <bool Q8, bool V2>
 __global__ void __launch_bounds__(128, 3)
 decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const uint8_t* __restrict__ k_q,
                          const float* __restrict__ k_s, const __half* __restrict__ v_hi, const uint8_t* __restrict__ v_q,
@@ -173,6 +183,9 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    __half2 qh[4];                                           // V2: the (scaled) query in fp16 for the residual term
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qh[i] = __floats2half2_rn(qr[2 * i], qr[2 * i + 1]);
     // this lane group's keys: key0 + w*4 + grp + 16*i
     for (int j0 = key0 + w * 4 + grp; j0 < key1 + 48; j0 += 64) {          // warp-uniform trip count
         uint4 kh[4], vh[4];
@@ -196,6 +209,54 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
                 }
             }
         }
+        if (V2) {
+            float sc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float kf[8];
+                unpack8(kh[u], kf);
+                float s = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s = fmaf(qr[e], kf[e], s);
+                if (Q8) {
+                    __half2 a2 = __floats2half2_rn(0.f, 0.f);
+                    a2 = __hfma2(qh[0], q8_pair(kq[u].x, 0), a2);
+                    a2 = __hfma2(qh[1], q8_pair(kq[u].x, 2), a2);
+                    a2 = __hfma2(qh[2], q8_pair(kq[u].y, 0), a2);
+                    a2 = __hfma2(qh[3], q8_pair(kq[u].y, 2), a2);
+                    const float2 f2 = __half22float2(a2);
+                    s = fmaf(f2.x + f2.y, ks[u], s);
+                }
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                sc[u] = (j0 + u * 16 < key1) ? s : -INFINITY;
+            }
+            if (j0 < key1) {                                  // uniform within the 8-lane group; key u = 0 is valid
+                const float mn = fmaxf(fmaxf(m, sc[0]), fmaxf(fmaxf(sc[1], sc[2]), sc[3]));
+                const float corr = expf(m - mn);              // exp(-inf) = 0 for the first block
+                l *= corr;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] *= corr;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float p = expf(sc[u] - mn);         // 0 for keys past the split
+                    float vf[8], t[8];
+                    unpack8(vh[u], vf);
+                    l += p;
+                    if (Q8) {
+                        unpack8q(vq[u], t);
+                        const float p2 = p * vs[u];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], fmaf(p2, t[e], acc[e]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
+                    }
+                }
+                m = mn;
+            }
+        } else {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u * 16;
@@ -233,6 +294,7 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
                 m = mn;
             }
         }
+        }   // !V2
     }
     // ---- combine the 16 lane groups of the CTA ----
     if (sub == 0) { s_m[w][grp] = m; s_l[w][grp] = l; }
@@ -529,12 +591,15 @@ int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int
                       __half* ol, float* of, cudaStream_t st) {
     const bool q8 = kv.k_q != nullptr;
     ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * (q8 ? 64 * 3.0 + 4.0 : 64 * 2.0));
-    if (q8)
-        STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<true>, dim3(XS, H, B), dim3(128), 0, st, q, kv.k_hi, kv.k_q, kv.k_s,
-                               kv.v_hi, kv.v_q, kv.v_s, d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
-    else
-        STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<false>, dim3(XS, H, B), dim3(128), 0, st, q, kv.k_hi, kv.k_q, kv.k_s,
-                               kv.v_hi, kv.v_q, kv.v_s, d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
+    static const bool v2 = []() { const char* e = getenv("STB_XATTN_V2"); return e && e[0] == '1'; }();
+#define STB_XATTN(Q, V)                                                                                                     \
+    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<Q, V>, dim3(XS, H, B), dim3(128), 0, st, q, kv.k_hi, kv.k_q, kv.k_s, kv.v_hi, \
+                           kv.v_q, kv.v_s, d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of))
+    if (q8 && v2) STB_XATTN(true, true);
+    else if (q8) STB_XATTN(true, false);
+    else if (v2) STB_XATTN(false, true);
+    else STB_XATTN(false, false);
+#undef STB_XATTN
     STB_LAUNCH_OK();
     return STB_OK;
 }
