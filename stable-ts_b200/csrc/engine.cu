@@ -422,7 +422,18 @@ struct StepWs {
     float* part;       // split-K partials [split][B][N] of the swapped tcgen05 decode linears
     size_t bytes;
 };
-constexpr int STEP_GEMV_MAX_B = 16;      // <= : mma.sync batched GEMV; above (up to 64): swapped split-K tcgen05 GEMM
+constexpr int STEP_GEMV_MAX_B = 16;      // <= : mma.sync batched GEMV; above: swapped split-K tcgen05 GEMM
+// tuning knobs for A/B runs (defaults are the measured choices): STB_STEP_GEMV_MAX_B = 0..64, STB_STEP_SPLIT_TILES = 1..160
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* e = getenv(name);
+    if (e == nullptr || e[0] == 0) return dflt;
+    const int v = atoi(e);
+    return v < lo ? lo : v > hi ? hi : v;
+}
+static int step_gemv_max_b() {
+    static const int v = env_int("STB_STEP_GEMV_MAX_B", STEP_GEMV_MAX_B, 0, 64);
+    return v;
+}
 constexpr int STEP_SPLITK_MAX_B = 128;    // sequences on the N side of one tcgen05 tile (BN = 16 / 32 / 64 / 128)
 constexpr int STEP_SPLITK_TILES = 160;   // bound on split * ceil(N / 128) (one tile per SM)
 static StepWs carve_step(const stb_model* m, int B, void* ws) {
@@ -438,7 +449,7 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.ln = take_split(c, (size_t)B * d, lo);
     w.attn = take_split(c, (size_t)B * d, lo);
     w.hid = take_split(c, (size_t)B * 4 * d, lo);
-    w.part = (B > STEP_GEMV_MAX_B && B <= STEP_SPLITK_MAX_B) ? c.take<float>((size_t)B * STEP_SPLITK_TILES * 128) : nullptr;
+    w.part = (B > step_gemv_max_b() && B <= STEP_SPLITK_MAX_B) ? c.take<float>((size_t)B * STEP_SPLITK_TILES * 128) : nullptr;
     w.bytes = c.off;
     return w;
 }
@@ -463,7 +474,8 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     //                  slices on the GEMM batch axis so that ~one tile lands on every SM; partials [split][B][N] stay in
     //                  L2 and splitk_finish_kernel adds bias / GELU / residual and the LayerNorm that follows
     //   > 128        : the plain tcgen05 GEMM (sequences on the M side)
-    const bool use_gemv = B <= STEP_GEMV_MAX_B, use_splitk = !use_gemv && B <= STEP_SPLITK_MAX_B;
+    const bool use_gemv = B <= step_gemv_max_b(), use_splitk = !use_gemv && B <= STEP_SPLITK_MAX_B;
+    static const int tile_budget = env_int("STB_STEP_SPLIT_TILES", sm_count(), 1, STEP_SPLITK_TILES);
     const Split none = {nullptr, nullptr};
     // ln_g != nullptr: also produce LayerNorm(out)*ln_g+ln_b into w.ln (only with a residual, out_f32 = w.x)
     auto lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
@@ -476,7 +488,7 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
             int split = 1;
             if (k % 64 == 0)
                 for (int sdiv = 1; sdiv <= nkb; ++sdiv)
-                    if (nkb % sdiv == 0 && (long long)mt * sdiv <= sm_count() && mt * sdiv <= STEP_SPLITK_TILES) split = sdiv;
+                    if (nkb % sdiv == 0 && (long long)mt * sdiv <= tile_budget && mt * sdiv <= STEP_SPLITK_TILES) split = sdiv;
             const bool direct = split == 1 && bias == nullptr && act == STB_ACT_NONE && res == nullptr && ln_g == nullptr &&
                                 out_split.hi == nullptr;
             const int ks = k / split;
