@@ -15,6 +15,11 @@ What is here
 ``oracle.stable_path``  restatement of the reference's own orchestration on the hot path
                         (stable_whisper/timing.py, decode.py, alignment.py:405-429,649-672).
 ``oracle/c``            plain-C restatement of the DTW and the width-7 median filter.
+``oracle.silence``      numpy restatement of the non-VAD silence detection (SURVEY.md section 8f row 1:
+                        stable_whisper/stabilization/nonvad.py, utils.py:43-111), pinned bit-exactly
+                        against PyTorch's operators, the live reference functions and fixtures written
+                        by the unmodified reference (oracle/make_golden_silence.py,
+                        tests/test_oracle_silence.py).
 
 Pinning status: the reference ships NO golden vectors for this path, so
 "parity pinned by the reference's own tests" is impossible ("parity unpinned" in that sense).
