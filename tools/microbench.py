@@ -3,6 +3,7 @@ rotating weight copies exceeds the 126 MB L2 so every launch streams its weights
 
     python tools/microbench.py gemv      # decode-step linear shapes of large-v3 at 16 / 64 sequences
     python tools/microbench.py dtw       # DTW at 16 / 64 windows x [101 x 1500]
+    python tools/microbench.py step 120 4   # ms per decode step (120 windows, 4 decoder layers of large-v3 width)
 """
 import json
 import os
@@ -125,9 +126,52 @@ def bench_dtw(batches=(16, 64, 148)):
     return out
 
 
+def bench_step(windows=120, layers=4, s1=24, s2=72):
+    """ms per KV-cached decode step of a large-v3-WIDTH model with `layers` decoder layers (cross K/V of 120 windows x 32
+    layers would not leave room for A/B runs), from the slope between two forced decodes of s1 and s2 steps (graph replay).
+    Use with STB_XATTN_V2 / STB_DECODE_CHAIN / STB_STEP_* to A/B the decode-step variants:  microbench.py step [windows] [layers]"""
+    import time
+    from stable_ts_b200.api import random_state_dict
+    from stable_ts_b200.decode import DecodingOptions, decode_windows
+    from stable_ts_b200.model import B200Whisper
+    from stable_ts_b200.tokenizer import get_tokenizer
+    from oracle.whisper_ref.model import ModelDimensions      # dims container only (tools/ is developer tooling)
+    dims = ModelDimensions(128, 1500, 1280, 20, 1, 51866, 448, 1280, 20, layers)
+    model = B200Whisper(dims, random_state_dict(dims, 0), device="cuda")
+    tk = get_tokenizer(model, language="en", task="transcribe", synthetic=True)
+    g = torch.Generator().manual_seed(0)
+    audio = (torch.randn(windows, 480000, generator=g) * 0.1).cuda()
+    enc = model.encode(model.log_mel(audio))
+    forced = torch.randint(300, 50000, (s2, windows), generator=g, dtype=torch.int32)
+
+    def run(steps):
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        decode_windows(model, tk, enc, DecodingOptions(language="en", sample_len=steps), forced_tokens=forced[:steps],
+                       reuse_buffers=True)
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t) * 1e3
+    run(s1)
+    a = min(run(s1) for _ in range(3))
+    b = min(run(s2) for _ in range(3))
+    per_step = (b - a) / (s2 - s1)
+    L.lib().stb_prof_enable(1)
+    decode_windows(model, tk, enc, DecodingOptions(language="en", sample_len=8), forced_tokens=forced[:8], use_graph=False,
+                   reuse_buffers=True)
+    prof = L.prof_report()
+    L.lib().stb_prof_enable(0)
+    table = {k: {"n": v["n"], "us_avg": round(v["ms"] * 1e3 / max(v["n"], 1), 2)} for k, v in prof.items()}
+    out = dict(windows=windows, layers=layers, ms_per_step=round(per_step, 3), ms_per_layer_step=round(per_step / layers, 4),
+               fixed_ms=round(a - per_step * s1, 1), eager_kernels=table)
+    print(out, flush=True)
+    return out
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gemv"
-    if what == "ncu":          # short run for `ncu -k regex:...`: fc1 / fc2 at 64 sequences + one DTW batch
+    if what == "step":
+        res = bench_step(*(int(v) for v in sys.argv[2:4]))
+    elif what == "ncu":          # short run for `ncu -k regex:...`: fc1 / fc2 at 64 sequences + one DTW batch
         res = [bench_gemv((64,), ((5120, 1280), (1280, 5120)), iters=4), bench_dtw((16,))]
     else:
         res = {"gemv": bench_gemv, "dtw": bench_dtw, "splitk": bench_splitk}[what]()
