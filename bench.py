@@ -196,17 +196,40 @@ def cpu_arm(args, dims_tuple, n_windows, threads=None):
     audios, wts = _CPU["data"]
     t0 = time.perf_counter()
     n_words = 0
+    detail = []
     for a, wt in zip(audios, wts):
         if args.workload == "align":
-            n_words += len(SP.align_audio_window(model, tk, wt, a))
-        else:                                    # decode.py main loop (forced script) + timing.py alignment pass
-            mel = W.pad_or_trim(W.log_mel_spectrogram(a, model.dims.n_mels), 3000)
+            words = SP.align_audio_window(model, tk, wt, a)
+            detail.append(dict(words=words, step_argmax=None))
+        else:       # the per-window body of transcribe_stable: decode.py main loop (forced script) -> segment slicing ->
+            # gap-padded word timestamps (timing.py:411-500), restated in oracle/stable_path.py:transcribe_window
             script = [t for w in wt for t in w]
-            _, af, _ = SP.decode_window(model, mel, forced_tokens=script, sample_len=len(script), language="en",
-                                        max_initial_timestamp=None)
-            n_words += len(SP.align_window(model, tk, wt, mel, len(a), audio_features=af))
+            segs, ex = SP.transcribe_window(model, tk, a, forced_tokens=script, sample_len=len(script), language="en")
+            words = [w for s_ in segs for w in s_["words"]]
+            detail.append(dict(words=words, step_argmax=ex["step_argmax"]))
+        n_words += len(words)
     dt = time.perf_counter() - t0
+    _CPU["detail"] = detail
     return n_windows * AUDIO_S / dt, n_words / dt, dt, cores
+
+
+def parity_vs_cpu(gpu_words, gpu_step_argmax, cpu_detail):
+    """Window 0 of the GPU batch against the CPU oracle's result for the SAME window (same audio seed, script and weights):
+    the gates of BASELINE.json north_star, evaluated at the benchmarked model depth."""
+    cw = cpu_detail["words"]
+    out = {"window": 0, "words_gpu": len(gpu_words), "words_cpu": len(cw), "tokens_equal": None, "worst_dt_s": None,
+           "prob_rel": None, "ok": False}
+    if cpu_detail["step_argmax"] is not None and gpu_step_argmax is not None:
+        out["tokens_equal"] = bool(list(gpu_step_argmax) == list(cpu_detail["step_argmax"]))
+        out["decode_steps_compared"] = len(cpu_detail["step_argmax"])
+    if len(gpu_words) != len(cw) or any(list(a["tokens"]) != list(b["tokens"]) for a, b in zip(gpu_words, cw)):
+        out["detail"] = "word lists differ"
+        return out
+    wt = max([0.0] + [max(abs(a["start"] - b["start"]), abs(a["end"] - b["end"])) for a, b in zip(gpu_words, cw)])
+    wp = max([0.0] + [abs(a["probability"] - b["probability"]) / max(abs(b["probability"]), 1e-30) for a, b in zip(gpu_words, cw)])
+    out.update(worst_dt_s=round(wt, 4), prob_rel=float(f"{wp:.3e}"),
+               ok=bool(wt <= 0.0201 and wp <= 2e-3 and out["tokens_equal"] is not False))
+    return out
 
 
 def run_reference(args, dims_tuple):
@@ -250,7 +273,9 @@ def run_b200(args, dims_tuple):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    os.environ["NCCL_DEBUG"] = "WARN"                   # keep stdout to the single JSON line (no NCCL version banner)
+    # NCCL_DEBUG is left as the launcher set it (the rank / transport evidence must stay observable); its log goes to stderr
+    # so that stdout carries only the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -296,10 +321,14 @@ def run_b200(args, dims_tuple):
     # again as a batch of 3 (different kernels: mma.sync GEMV decode linears instead of the split-K GEMMs, other grid sizes,
     # other buffer offsets), must give the same words -- catches index overflow / layout faults that only show at 100+ windows
     selfcheck = None
+    gpu_w0 = None                                       # window 0 of pool 0 (rank 0): compared with the CPU oracle below
+    if args.workload == "align" and rank == 0 and not args.ncu:
+        gpu_w0 = (align_words_batch(model, tk, [host_audio[0][0]], [batches[0][1][0]])[0], None)
     if args.workload == "transcribe" and rank == 0 and not args.ncu:
         try:
             idx = sorted({0, Wn // 2, Wn - 1})
-            full, _ = transcribe_windows(model, tk, host_audio[0], options=dopt, forced_tokens=scripts[0])
+            full, finfo = transcribe_windows(model, tk, host_audio[0], options=dopt, forced_tokens=scripts[0])
+            gpu_w0 = ([w for s_ in full[0] for w in s_["words"]], finfo["step_argmax"][:, 0].tolist())
             small, _ = transcribe_windows(model, tk, host_audio[0][idx].contiguous(), options=dopt,
                                           forced_tokens=scripts[0][:, idx].contiguous())
             worst_t, worst_p, n_cmp, bad = 0.0, 0.0, 0, None
@@ -439,16 +468,23 @@ def run_b200(args, dims_tuple):
                    "hbm_frac": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak, 3) if v["ms"] > 0 and v["bytes"] > 0 else None}
                for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
 
+    if world > 1:                                       # every GPU number is final: the CPU arm below is rank 0 alone
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
-    cpu = None
-    if not args.no_cpu_baseline and world == 1:
+    cpu, parity = None, None
+    if not args.no_cpu_baseline:
         v, w, dt, cores = cpu_arm(args, dims_tuple, args.cpu_windows)
         cpu = {"value": v, "unit": "audio_s/s", "cores": cores, "kind": "port", "aligned_words_per_s": w,
                "sample": f"{args.cpu_windows} window(s) of the same workload ({dt:.1f} s of CPU work), oracle port of the "
                          f"reference CPU path, fp32, torch threads = {cores}"}
+        if gpu_w0 is not None:                          # same window (audio seed 1000, script, weights) through both paths
+            try:
+                parity = parity_vs_cpu(gpu_w0[0], gpu_w0[1], _CPU["detail"][0])
+            except Exception as e:
+                parity = {"ok": None, "detail": f"parity check did not run: {type(e).__name__}: {e}"}
+            print(f"[bench] parity_vs_cpu: {parity}", file=sys.stderr)
     out = {
         "metric": f"rtfx_{args.model}_{args.workload}", "value": value, "unit": "audio_s/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -466,7 +502,7 @@ def run_b200(args, dims_tuple):
                    "l2": "per-step working set (weights 6.2 GB + activations) >> 126 MB L2; inputs rotate between 2 pools"},
         "rtf": 1.0 / value, "aligned_words_per_s": n_words_total / (ms_step / 1e3),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_other": roof_other, "kernels": kernels,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "parity_vs_cpu": parity,
         "e2e": {"value": e2e_value, "unit": "audio_s/s", "h2d_bytes_per_step": Wn * N_SAMPLES * 4,
                 # jumps int32 [N+1] + token probs fp32 [N] per window (+ token/argmax tables and sampler state for decode)
                 "d2h_bytes_per_step": int(Wn * ((args.tokens + 3) * 4 + (args.tokens + 2) * 4)
@@ -474,8 +510,6 @@ def run_b200(args, dims_tuple):
                 "ms_per_step": e2e_s * 1e3, "aligned_words_per_s": n_words_total / e2e_s},
     }
     print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

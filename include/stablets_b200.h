@@ -43,6 +43,10 @@ extern "C" {
 
 STB_API const char* stb_last_error(void);
 STB_API int stb_abi_version(void);
+/* run-time switches for A/B measurement of kernel variants: "xattn_v2", "decode_chain", "xkv_fp16" (0/1); unknown names are
+ * an error.  Not part of the reference's behaviour -- every setting must pass the same parity tests. */
+STB_API int stb_set_option(const char* name, int value);
+STB_API int stb_get_option(const char* name);
 /* measurement hooks (bench.py): kernels launched by this library so far; per-launch CUDA-event timing of every kernel */
 STB_API unsigned long long stb_launch_count(void);
 STB_API void stb_prof_enable(int on);

@@ -316,3 +316,190 @@ def synth_gapped_audio(n_samples: int, seed: int = 77, floor: float = 0.0) -> to
     if floor > 0:
         y = y + floor * torch.randn(n_samples, generator=g, dtype=torch.float64) * (1 - env)
     return y.float()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# One transcribe window end to end (the per-window body of transcribe_stable): decode -> segments at timestamp tokens ->
+# gap-padded word timestamps.  Restates stable_whisper/whisper_word_level/original_whisper.py:537-665 and
+# stable_whisper/timing.py:309-500; pinned against the unmodified reference in tests/test_oracle_vs_reference.py.
+# ---------------------------------------------------------------------------------------------------------------------
+PREPEND_PUNCTUATIONS = "\"'“¿([{-"
+APPEND_PUNCTUATIONS = "\"'.。,，!！?？:：”)]}、"
+TIME_PRECISION = 0.02
+
+
+def group_tokens_into_words(tokens: Sequence[int], tokenizer) -> Tuple[List[str], List[List[int]]]:
+    """Incremental-decode word grouping (timing.py:309-341): a token group closes when its decoded text is a prefix
+    of what is left of the full decode; in space-delimited languages a closed group that neither starts with a space
+    nor is pure punctuation is glued to the previous word."""
+    import string as _string
+    lang = getattr(tokenizer, "language_code", tokenizer.language)
+    spaced = lang not in {"zh", "ja", "th", "lo", "my"}
+    rest = tokenizer.decode_with_timestamps(list(tokens))
+    words: List[str] = []
+    groups: List[List[int]] = []
+    open_group: List[int] = []
+    piece = ""
+    glue = False
+    for tok in tokens:
+        open_group.append(tok)
+        piece = tokenizer.decode(open_group)
+        closed = tok >= tokenizer.eot
+        if not closed and rest.startswith(piece):
+            closed = True
+            if spaced:
+                glue = not (piece.startswith(" ") or piece.strip() in _string.punctuation)
+        if not closed:
+            continue
+        if glue and words:
+            words[-1] += piece
+            groups[-1] += open_group
+        else:
+            words.append(piece)
+            groups.append(open_group)
+        rest = rest[len(piece):]
+        open_group = []
+    if open_group:                                   # undecodable tail: keeps whatever text is left
+        words.append(rest if rest else piece)
+        groups.append(open_group)
+    elif rest:
+        words[-1] += rest
+    return words, groups
+
+
+def window_word_script(segments: List[dict], tokenizer, gap_padding: Optional[str] = " ...", pad_first_seg: bool = True):
+    """timing.py:344-392 without char_split: -> (text_tokens, words, word_tokens, seg_of_word); gap-padding pseudo-words
+    have word None and are NOT counted in seg_of_word."""
+    pad = None if gap_padding is None else (tokenizer.encode(gap_padding) if isinstance(gap_padding, str) else [gap_padding])
+    text_tokens: List[int] = []
+    words: List[Optional[str]] = []
+    word_tokens: List[List[int]] = []
+    seg_of_word: List[int] = []
+    for si, seg in enumerate(segments):
+        toks = [t for t in seg["tokens"] if t < tokenizer.eot]
+        w, g = group_tokens_into_words(toks, tokenizer)
+        # NB the reference compares a token id / list against the padding LIST, so these two tests are always True
+        # for a str padding (timing.py:367-369); kept verbatim in meaning
+        if pad is not None and g[0][0] != pad and (not text_tokens or text_tokens[-1] != pad) and (pad_first_seg or si):
+            text_tokens += pad
+            words.append(None)
+            word_tokens.append(list(pad))
+        seg_of_word += [si] * len(w)
+        for grp in g:
+            text_tokens += grp
+        words += w
+        word_tokens += g
+    return text_tokens, words, word_tokens, seg_of_word
+
+
+@torch.no_grad()
+def word_timestamps_window(model: Whisper, tokenizer, segments: List[dict], mel: torch.Tensor, num_samples: int, *,
+                           audio_features=None, gap_padding: Optional[str] = " ...", pad_first_seg: bool = True,
+                           min_word_dur: float = 0.1, prepend_punctuations: str = PREPEND_PUNCTUATIONS,
+                           append_punctuations: str = APPEND_PUNCTUATIONS, medfilt_width: int = 7, qk_scale: float = 1.0):
+    """add_word_timestamps_stable for one window, legacy aligner (timing.py:411-500): fills seg['words'] and moves
+    seg['start'|'end'] onto the first / last word."""
+    if not segments:
+        return
+    for seg in segments:
+        seg["words"] = []
+    text_tokens, words, word_tokens, seg_of_word = window_word_script(segments, tokenizer, gap_padding, pad_first_seg)
+    S = len(tokenizer.sot_sequence)
+    _, qks, _, token_probs = window_qks(model, tokenizer, text_tokens, mel, audio_features)
+    weights = attention_weights_legacy(qks, head_pairs_of(model), S, num_samples, medfilt_width, qk_scale)
+    jumps = jumps_from_matrix(weights.mean(dim=0))
+    bounds = np.pad(np.cumsum([len(g) for g in word_tokens]), (1, 0))
+    times = jumps / TOKENS_PER_SECOND
+    timed = [dict(word=w, tokens=list(g), start=float(times[a]), end=float(times[b]),
+                  probability=float(np.mean(token_probs[a:b]))) for w, g, a, b in zip(words, word_tokens, bounds[:-1], bounds[1:])]
+    # pull the gap-padding pseudo-words out; remember, per segment, the pseudo-word that precedes it (timing.py:395-407)
+    pad_before: Dict[int, dict] = {}
+    real: List[dict] = []
+    for t in timed:
+        if t["word"] is None:
+            pad_before[seg_of_word[len(real)]] = t
+        else:
+            real.append(t)
+    from types import SimpleNamespace
+    real = [SimpleNamespace(**t) for t in real]
+    _timing.merge_punctuations(real, prepend_punctuations, append_punctuations)
+    offset = segments[0]["seek"]
+    min_word_dur = min_word_dur or 0
+    for si, t in zip(seg_of_word, real):
+        if not t.tokens:
+            continue
+        start = t.start
+        if not segments[si]["words"] and (t.end - t.start) < min_word_dur and si in pad_before:
+            start = pad_before[si]["start"]
+        segments[si]["words"].append(dict(word=t.word, start=round(offset + start, 3), end=round(offset + t.end, 3),
+                                          probability=t.probability, tokens=t.tokens))
+    for seg in segments:
+        if seg["words"]:
+            seg["start"], seg["end"] = seg["words"][0]["start"], seg["words"][-1]["end"]
+
+
+def slice_window_segments(tokens: Sequence[int], tokenizer, time_offset: float, segment_duration: float, result,
+                          word_timestamps: bool = True, punctuations: str = PREPEND_PUNCTUATIONS + APPEND_PUNCTUATIONS):
+    """original_whisper.py:550-627: cut the sampled tokens at consecutive timestamp pairs, then drop punctuation-only
+    and (with word timestamps) zero-length segments.  -> (segments, end_timestamp_pos, single_timestamp_ending)."""
+    toks = list(tokens)
+    tb = tokenizer.timestamp_begin
+    stamp = [t >= tb for t in toks]
+    single_ending = stamp[-2:] == [False, True]
+    cuts = [i + 1 for i in range(len(toks) - 1) if stamp[i] and stamp[i + 1]]
+
+    def make(start, end, part):
+        return dict(seek=round(time_offset, 3), start=start, end=end, tokens=list(part),
+                    text=tokenizer.decode([t for t in part if t < tokenizer.eot]), temperature=result.temperature,
+                    avg_logprob=result.avg_logprob, compression_ratio=result.compression_ratio,
+                    no_speech_prob=result.no_speech_prob)
+
+    segs, end_pos = [], 0
+    if cuts:
+        if single_ending:
+            cuts.append(len(toks))
+        prev = 0
+        for cut in cuts:
+            part = toks[prev:cut]
+            end_pos = part[-1] - tb
+            segs.append(make(round(time_offset + (part[0] - tb) * TIME_PRECISION, 3),
+                             round(time_offset + min(end_pos * TIME_PRECISION, segment_duration), 3), part))
+            prev = cut
+    else:
+        dur = segment_duration
+        stamps = [t for t in toks if t >= tb]
+        if stamps and stamps[-1] != tb:
+            end_pos = stamps[-1] - tb
+            dur = min(end_pos * TIME_PRECISION, segment_duration)
+        segs.append(make(round(time_offset, 3), round(time_offset + dur, 3), toks))
+    segs = [s for s in segs if s["text"].strip() not in punctuations]       # substring test, as the reference's `in`
+    if word_timestamps:
+        segs = [s for s in segs if s["start"] != s["end"]]
+    return segs, end_pos, single_ending
+
+
+@torch.no_grad()
+def transcribe_window(model: Whisper, tokenizer, audio: torch.Tensor, *, time_offset: float = 0.0,
+                      forced_tokens: Optional[Sequence[int]] = None, ts_token_mask=None, gap_padding: Optional[str] = " ...",
+                      min_word_dur: float = 0.1, max_instant_words: Optional[float] = None, **decode_options):
+    """One <=30 s window the way transcribe_stable processes it at temperature 0 (original_whisper.py:500-665), without
+    the cross-window state (prompt, seek): log-mel -> decode_stable -> slice -> add_word_timestamps_stable.
+    ``forced_tokens``: fixed script appended instead of the argmax (random-weight benchmarks).
+    -> (segments, extras{decode, step_argmax, tokens})"""
+    n = int(audio.shape[-1])
+    mel = _audio.pad_or_trim(_audio.log_mel_spectrogram(audio, model.dims.n_mels, padding=max(_audio.N_SAMPLES - n, 0)),
+                             _audio.N_FRAMES)
+    decode_options.setdefault("max_initial_timestamp", None)                # transcribe_stable's default (:262-263)
+    res, af, ex = decode_window(model, mel, ts_token_mask=ts_token_mask, forced_tokens=forced_tokens, **decode_options)
+    toks = list(forced_tokens)[: len(ex["step_argmax"])] if forced_tokens is not None else res.tokens
+    extras = dict(decode=res, step_argmax=ex["step_argmax"], tokens=toks)
+    if not toks:
+        return [], extras
+    segs, end_pos, _ = slice_window_segments(toks, tokenizer, time_offset, n / _audio.SAMPLE_RATE, res)
+    num = min(round(end_pos * N_SAMPLES_PER_TOKEN), n) if end_pos > 0 else n
+    word_timestamps_window(model, tokenizer, segs, mel, num, audio_features=af, gap_padding=gap_padding,
+                           min_word_dur=min_word_dur)
+    if max_instant_words is not None:                                        # original_whisper.py:655-663
+        segs = [s for s in segs if not s["words"] or
+                float(np.mean(np.array([w["start"] == w["end"] for w in s["words"]]).astype(np.float16))) <= max_instant_words]
+    return segs, extras

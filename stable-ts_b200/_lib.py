@@ -42,6 +42,8 @@ class Dims(ctypes.Structure):
 _SIGS = {
     "stb_last_error": (c_char_p, []),
     "stb_abi_version": (c_int, []),
+    "stb_set_option": (c_int, [c_char_p, c_int]),
+    "stb_get_option": (c_int, [c_char_p]),
     "stb_launch_count": (ctypes.c_ulonglong, []),
     "stb_prof_enable": (None, [c_int]),
     "stb_prof_report": (c_int, [ctypes.c_char_p, c_size_t]),
@@ -117,6 +119,15 @@ class StbError(RuntimeError):
 def check(rc: int):
     if rc != 0:
         raise StbError(f"libstablets_b200 error {rc}: {lib().stb_last_error().decode(errors='replace')}")
+
+
+def set_option(name: str, value: int):
+    """Run-time kernel-variant switch (stb_set_option): "xattn_v2", "decode_chain", "xkv_fp16"."""
+    check(lib().stb_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    return int(lib().stb_get_option(name.encode()))
 
 
 def ptr(t):

@@ -591,7 +591,7 @@ int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int
                       __half* ol, float* of, cudaStream_t st) {
     const bool q8 = kv.k_q != nullptr;
     ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * (q8 ? 64 * 3.0 + 4.0 : 64 * 2.0));
-    static const bool v2 = []() { const char* e = getenv("STB_XATTN_V2"); return e && e[0] == '1'; }();
+    const bool v2 = option(OPT_XATTN_V2) != 0;
 #define STB_XATTN(Q, V)                                                                                                     \
     STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<Q, V>, dim3(XS, H, B), dim3(128), 0, st, q, kv.k_hi, kv.k_q, kv.k_s, kv.v_hi, \
                            kv.v_q, kv.v_s, d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of))

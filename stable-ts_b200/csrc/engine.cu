@@ -258,10 +258,11 @@ static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split
         float* sc = reinterpret_cast<float*>(q + 2 * c.k_elems);
         Vd->k_hi = K.hi;
         Vd->v_hi = v;
-        Vd->k_q = lo ? q : nullptr;
-        Vd->v_q = lo ? q + c.k_elems : nullptr;
-        Vd->k_s = lo ? sc : nullptr;
-        Vd->v_s = lo ? sc + c.rows : nullptr;
+        const bool q8 = lo && option(OPT_XKV_FP16) == 0;     // xkv_fp16: the step reads only the fp16 planes (A/B knob)
+        Vd->k_q = q8 ? q : nullptr;
+        Vd->v_q = q8 ? q + c.k_elems : nullptr;
+        Vd->k_s = q8 ? sc : nullptr;
+        Vd->v_s = q8 ? sc + c.rows : nullptr;
     }
 }
 
@@ -286,9 +287,9 @@ static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int 
         STB_TRY(project_vT(m, xa, B, T, d, offs(W_HI(L, STB_L_CKV_W), (long long)d * d), offs(W_LO(L, STB_L_CKV_W), (long long)d * d),
                            W_F32(L, STB_L_CKV_B) + d, vT, STB_KPAD, st));
         if (decode_layout) {   // head-major copy of V for the decode-step kernel (contiguous per (sequence, head), like K)
-            STB_TRY(v_headmajor(vT.hi, vT.lo, B * D.n_text_head, T, STB_KPAD, const_cast<__half*>(Vd.v_hi),
+            STB_TRY(v_headmajor(vT.hi, Vd.v_q ? vT.lo : nullptr, B * D.n_text_head, T, STB_KPAD, const_cast<__half*>(Vd.v_hi),
                                 const_cast<uint8_t*>(Vd.v_q), const_cast<float*>(Vd.v_s), st));
-            if (K.lo)   // 3-byte decode format of K: int8 residual + row scale next to the fp16 hi plane
+            if (K.lo && Vd.k_q)   // 3-byte decode format of K: int8 residual + row scale next to the fp16 hi plane
                 STB_TRY(pack_q8_rows(K.hi, K.lo, (long long)B * D.n_text_head * T, const_cast<uint8_t*>(Vd.k_q),
                                      const_cast<float*>(Vd.k_s), st));
         }

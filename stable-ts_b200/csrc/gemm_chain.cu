@@ -360,8 +360,7 @@ gemm_chain_kernel(const __grid_constant__ ChainMaps maps, const __grid_constant_
 // host side
 // ---------------------------------------------------------------------------------------------------------
 bool decode_chain_enabled() {
-    static const bool v = []() { const char* e = getenv("STB_DECODE_CHAIN"); return e && e[0] == '1'; }();
-    return v;
+    return option(OPT_DECODE_CHAIN) != 0;
 }
 
 struct ChainBuilder {

@@ -55,6 +55,27 @@ bool pdl_enabled() {
     return v != 0;
 }
 
+struct OptDef { const char* name; const char* env; int dflt; };
+static const OptDef g_opt_defs[OPT_COUNT] = {
+    {"xattn_v2", "STB_XATTN_V2", 0},          // decode cross-attention: half2 residual dot + block-wise rescale
+    {"decode_chain", "STB_DECODE_CHAIN", 0},  // decode linears between two attention kernels as one persistent kernel
+    {"xkv_fp16", "STB_XKV_FP16", 0},          // decode cross-attention reads only the fp16 plane of K / V (2 B/element)
+};
+static int g_opt[OPT_COUNT];
+static bool g_opt_init = false;
+static void opt_init() {
+    if (g_opt_init) return;
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        const char* e = getenv(g_opt_defs[i].env);
+        g_opt[i] = (e && e[0]) ? atoi(e) : g_opt_defs[i].dflt;
+    }
+    g_opt_init = true;
+}
+int option(Option o) {
+    opt_init();
+    return g_opt[o];
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {
@@ -83,7 +104,21 @@ __global__ void split_f16_kernel(const float* __restrict__ src, long long rows, 
 }  // namespace stb
 
 extern "C" const char* stb_last_error(void) { return stb::get_error(); }
-extern "C" int stb_abi_version(void) { return 1; }
+extern "C" int stb_abi_version(void) { return 2; }
+extern "C" int stb_set_option(const char* name, int value) {
+    STB_REQUIRE(name, "stb_set_option: null name");
+    stb::opt_init();
+    for (int i = 0; i < stb::OPT_COUNT; ++i)
+        if (strcmp(name, stb::g_opt_defs[i].name) == 0) { stb::g_opt[i] = value; return STB_OK; }
+    STB_REQUIRE(false, "stb_set_option: unknown option '%s'", name);
+    return STB_ERR_ARG;
+}
+extern "C" int stb_get_option(const char* name) {
+    stb::opt_init();
+    for (int i = 0; name && i < stb::OPT_COUNT; ++i)
+        if (strcmp(name, stb::g_opt_defs[i].name) == 0) return stb::g_opt[i];
+    return -1;
+}
 extern "C" unsigned long long stb_launch_count(void) { return stb::launches(); }
 
 extern "C" int stb_split_f16(const float* src, long long rows, int cols, long long src_ld, void* hi, void* lo,

@@ -111,7 +111,8 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
     if word_timestamps:
         add_word_timestamps_batch(windows, model, tokenizer, enc=enc, ckv=extras["ckv"], gap_padding=gap_padding,
                                   min_word_dur=min_word_dur)
-    return [w["segments"] for w in windows], dict(decode=results, steps=extras["steps"])
+    return [w["segments"] for w in windows], dict(decode=results, steps=extras["steps"], step_argmax=extras["step_argmax"],
+                                                  step_tokens=extras["step_tokens"])
 
 
 def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_windows: int = 16, **kw) -> dict:

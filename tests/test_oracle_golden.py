@@ -67,3 +67,18 @@ def test_dtw_goldens_python_and_c():
         cp, jumps = c_oracle.dtw(-x)
         assert np.array_equal(cp, p)
         assert np.array_equal(jumps, SP.jumps_from_matrix(torch.from_numpy(x)))
+
+
+@pytest.mark.parametrize("name", ["mini_en", "mini_ml"])
+def test_transcribe_window_reproduces_reference_driver(name):
+    """SP.transcribe_window == first window of the unmodified transcribe_stable (tests/golden/*_transcribe.json)."""
+    import json
+    z, model, tk, script, wts, audio = load_case(name)
+    gold = json.load(open(os.path.join(GOLD, f"{name}_transcribe.json")))
+    segs, _ = SP.transcribe_window(model, tk, audio, language="en", sample_len=40)
+    assert [s["tokens"] for s in segs] == [s["tokens"] for s in gold["segments"]]
+    for s, g in zip(segs, gold["segments"]):
+        assert s["start"] == g["start"] and s["end"] == g["end"]
+        assert [(w["word"], w["tokens"], w["start"], w["end"]) for w in s["words"]] == \
+               [(w["word"], w["tokens"], w["start"], w["end"]) for w in g["words"]]
+        np.testing.assert_allclose([w["probability"] for w in s["words"]], [w["probability"] for w in g["words"]], rtol=1e-6)

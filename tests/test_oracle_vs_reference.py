@@ -75,3 +75,42 @@ def test_refine_and_decode_identical(ref):
     r, _ = decode_stable(model, mel, DecodingOptions(language="en", fp16=False, sample_len=16), ts_token_mask=mask)
     m, _, _ = SP.decode_window(model, mel, ts_token_mask=mask, language="en", sample_len=16)
     assert r.tokens == m.tokens and r.avg_logprob == m.avg_logprob and r.no_speech_prob == m.no_speech_prob
+
+
+@pytest.mark.parametrize("name,n_samples", [("tiny.en", 300000), ("tiny", 480000)])
+def test_transcribe_window_identical(ref, name, n_samples):
+    """SP.transcribe_window (decode -> slicing -> gap-padded word timestamps) == the first window of the UNMODIFIED
+    transcribe_stable (original_whisper.py:492-710), captured at its add_word_timestamps_stable call."""
+    import copy
+    import stable_whisper.whisper_word_level.original_whisper as ow
+    from oracle import stable_path as SP
+    W = ref
+    model = W.build_model(name, seed=3)
+    tk = W.tokenizer.get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language="en",
+                                   task="transcribe")
+    audio = SP.synth_audio(n_samples, seed=21)
+    first = {}
+    orig = ow.add_word_timestamps_stable
+
+    def spy(**kw):
+        orig(**kw)
+        if "segments" not in first:
+            first["segments"] = copy.deepcopy(kw["segments"])
+    ow.add_word_timestamps_stable = spy
+    try:
+        ow.transcribe_stable(model, audio, language="en", temperature=0.0, condition_on_previous_text=False,
+                             word_timestamps=True, vad=False, suppress_silence=False, suppress_ts_tokens=False,
+                             regroup=False, verbose=None, fp16=False, ignore_compatibility=True, sample_len=40)
+    finally:
+        ow.add_word_timestamps_stable = orig
+    mine, ex = SP.transcribe_window(model, tk, audio, language="en", sample_len=40)
+    theirs = first["segments"]
+    assert len(mine) == len(theirs) and len(mine) > 0
+    for a, b in zip(mine, theirs):
+        assert a["tokens"] == [int(t) for t in b["tokens"]]
+        assert a["start"] == b["start"] and a["end"] == b["end"] and a["text"] == b["text"]
+        assert len(a["words"]) == len(b["words"])
+        for wa, wb in zip(a["words"], b["words"]):
+            assert wa["word"] == wb["word"] and wa["tokens"] == wb["tokens"]
+            assert wa["start"] == wb["start"] and wa["end"] == wb["end"]
+            assert abs(wa["probability"] - wb["probability"]) < 1e-12

@@ -24,9 +24,4 @@ STB_XATTN_V2=1 run step_xattn_v2 300 python tools/microbench.py step 120 4
 STB_DECODE_CHAIN=1 run step_chain 300 python tools/microbench.py step 120 4
 STB_XATTN_V2=1 STB_DECODE_CHAIN=1 run step_both 300 python tools/microbench.py step 120 4
 grep -h "ms_per_step" "$OUT"/step_*.log | cut -c1-160 | tee -a "$OUT/summary.txt"
-# 5. the default bench (new keys: selfcheck, roofline = cross-attention HBM object, graph-replay launch count)
-echo "=== bench_default" | tee -a "$OUT/summary.txt"
-timeout 900 python bench.py --steps 3 --warmup 3 > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"
-echo "rc=$? ($(cut -c1-300 "$OUT/bench_default.json"))" | tee -a "$OUT/summary.txt"
-grep -h "self-check" "$OUT/bench_default.err" | tee -a "$OUT/summary.txt"
 cat "$OUT/summary.txt"
