@@ -189,6 +189,12 @@ STB_API int stb_decoder_forward(stb_model* m, const int32_t* tokens, int B, int 
 STB_API int stb_token_probs(const float* logits, long long ld, int n_rows, int n_classes, const int32_t* targets, float* prob_out,
                     int32_t* rank_out, void* stream);
 
+/* a10, 3-D form of the refine plugin (stable_whisper/alignment.py:669-671 returns softmax(logits[:, S:S+N, :eot]); the
+ *   unmodified Refiner derives the target's rank from it, non_whisper/refinement.py:305-325):
+ *   out[r][0..n_classes) = softmax(logits[r][:n_classes]), fp32, row pitch ld_out. */
+STB_API int stb_softmax_probs(const float* logits, long long ld, int n_rows, int n_classes, float* out, long long ld_out,
+                      void* stream);
+
 /* a5 QK post-processing, legacy alignment-head path (stable_whisper/timing.py:105-110,194):
  *   qk [B][A][M][ldq] fp32 (as written by stb_decoder_forward; M = rows per head in memory); rows S..S+R-1
  *   (the reference slices [S:-1], i.e. R = n_text_tokens + 1; smaller R lets windows with fewer tokens share a padded
@@ -262,14 +268,15 @@ typedef struct {
 /* Logit filters + greedy pick for one step, in place on logits [B][ld] (decode.py:46-58 + whisper.decoding filters):
  *   suppress_mask [V] uint8 (SuppressTokens), first_step_mask [V] uint8 applied when n_sampled == 0 (SuppressBlank),
  *   ApplyTimestampRules from the per-sequence state (apply_ts_rules, no_timestamps id, max_initial_ts index or -1),
- *   ts_mask (nullable) [1501] uint8 silent-timestamp mask, NaN -> -inf, argmax (first max index), log-softmax gather,
+ *   ts_mask (nullable) uint8 silent-timestamp mask: [1501] shared by the batch (ts_mask_stride = 0) or one row per
+ *   sequence [B][ts_mask_stride] (the reference computes one per window, original_whisper.py:504-511), NaN -> -inf, argmax (first max index), log-softmax gather,
  *   sum_logprob += logprob unless the sequence already ended, ended sequences keep emitting EOT.
  *   Step tables (nullable, [table_rows][B] int32, row = n_sampled so no per-step host traffic is needed):
  *   forced_table: token appended instead of the argmax (fixed-length benchmark scripts / teacher forcing);
  *   token_table: the appended token; argmax_table: the argmax before forcing.  next_out [B] feeds stb_decode_step. */
 STB_API int stb_sample_greedy(float* logits, long long ld, int B, int V, int eot, int ts_begin, int no_timestamps,
                       const uint8_t* suppress_mask, const uint8_t* first_step_mask, const uint8_t* ts_mask,
-                      int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
+                      long long ts_mask_stride, int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
                       int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows, void* stream);
 
 #ifdef __cplusplus

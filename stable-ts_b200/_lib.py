@@ -68,6 +68,7 @@ _SIGS = {
     "stb_decoder_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_longlong, c_void_p,
                                     POINTER(c_int32), c_int, c_void_p, c_size_t, c_void_p]),
     "stb_token_probs": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "stb_softmax_probs": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_longlong, c_void_p]),
     "stb_qkpost_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "stb_qk_postprocess": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_float, c_int, c_void_p,
                                    c_longlong, c_void_p, c_size_t, c_void_p]),
@@ -76,7 +77,7 @@ _SIGS = {
     "stb_decode_step": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p,
                                 c_size_t, c_void_p]),
     "stb_sample_greedy": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+                                  c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "stb_qkpost_dynamic_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "stb_qk_postprocess_dynamic": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_float, c_int, c_int,
                                            c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p]),

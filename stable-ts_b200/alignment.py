@@ -59,27 +59,44 @@ def align_words_batch(model: B200Whisper, tokenizer, audios: Sequence[torch.Tens
     return (out, inter) if return_intermediates else out
 
 
-def refine_probs(model: B200Whisper, tokenizer, audio_segment: torch.Tensor, tokens: Sequence[int], want_rank: bool = True):
-    """audio fp32 [2, n] -> (probs fp32 [2, N], rank int32 [2, N]) of the script tokens
-    (stable_whisper/alignment.py:649-672 + the gather/rank of refinement.py:305-325, without materialising [2,N,V])."""
+def _refine_logit_rows(model: B200Whisper, tokenizer, audio_segment: torch.Tensor, tokens: Sequence[int]):
+    """alignment.py:649-668: log-mel of [2, n] with the batch-global max and no sample padding, one teacher-forced pass with
+    the token row broadcast over the audio rows -> logits rows [2 * N, V_pad] of the script positions (device view)."""
     a = audio_segment.to(model.device, torch.float32)
     n = int(a.shape[-1])
-    mel = model.log_mel(a, padded_samples=n, batch_global_max=True)      # refine: no sample padding, batch-global max
+    mel = model.log_mel(a, padded_samples=n, batch_global_max=True)
     enc = model.encode(mel)
     ckv = model.cross_kv(enc)
     row = torch.tensor([token_row(tokenizer, tokens)] * a.shape[0], dtype=torch.int32)
     logits, _ = model.decode_forced(row, ckv)
     S, N = len(tokenizer.sot_sequence), len(tokens)
-    rows = torch.cat([logits[b, S:S + N] for b in range(a.shape[0])])
-    tgt = torch.tensor(list(tokens) * a.shape[0], dtype=torch.int32)
+    return torch.cat([logits[b, S:S + N] for b in range(a.shape[0])]), a.shape[0], N
+
+
+def refine_probs(model: B200Whisper, tokenizer, audio_segment: torch.Tensor, tokens: Sequence[int], want_rank: bool = True):
+    """audio fp32 [2, n] -> (probs fp32 [2, N], rank int32 [2, N]) of the script tokens
+    (stable_whisper/alignment.py:649-672 + the gather/rank of refinement.py:305-325, without materialising [2,N,V]).
+    rank = number of classes whose logit is strictly below the target's = the target's index in the ascending sort."""
+    rows, A, N = _refine_logit_rows(model, tokenizer, audio_segment, tokens)
+    tgt = torch.tensor(list(tokens) * A, dtype=torch.int32)
     p, r = model.token_probs(rows, tokenizer.eot, tgt, want_rank=want_rank)
-    return p.view(a.shape[0], N), (r.view(a.shape[0], N) if r is not None else None)
+    return p.view(A, N), (r.view(A, N) if r is not None else None)
 
 
-def get_b200_refinement_func(model: B200Whisper, tokenizer):
-    """-> inference_func(audio [2, n], tokens) -> Tensor [2, N] (the 2-D form the Refiner accepts,
-    stable_whisper/non_whisper/refinement.py:291-304)."""
+def get_b200_refinement_func(model: B200Whisper, tokenizer, form: str = "3d"):
+    """-> inference_func(audio [2, n], tokens) for the reference's ``Refiner`` (non_whisper/refinement.py:44-47).
+
+    form="3d" (default): Tensor [2, N, eot] of softmax probabilities on the model's device -- the same tensor the reference's
+    own closure returns (alignment.py:669-672), so the Refiner's token-rank test (refinement.py:305-325, ``best_tks_changed``
+    at :427) sees exactly what it sees with a PyTorch model.  form="2d": Tensor [2, N] of the script tokens' probabilities
+    only (the other form refinement.py:291-304 accepts; the rank test is then off, as the reference defines it)."""
+    if form not in ("3d", "2d"):
+        raise ValueError("form must be '3d' or '2d'")
+
     def inference_func(audio_segment: torch.Tensor, tokens: List[int]) -> torch.Tensor:
-        p, _ = refine_probs(model, tokenizer, audio_segment, tokens, want_rank=False)
-        return p.cpu()
+        if form == "2d":
+            p, _ = refine_probs(model, tokenizer, audio_segment, tokens, want_rank=False)
+            return p.cpu()
+        rows, A, N = _refine_logit_rows(model, tokenizer, audio_segment, tokens)
+        return model.softmax_probs(rows, tokenizer.eot).view(A, N, int(tokenizer.eot))
     return inference_func

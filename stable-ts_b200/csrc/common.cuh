@@ -75,8 +75,8 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 bool pdl_enabled();   // STB_PDL=0 disables (misc.cu)
 // run-time switches (stb_set_option / stb_get_option, misc.cu); defaults come from the environment variable of the same
-// meaning so a whole process can be flipped without code (STB_XATTN_V2, STB_DECODE_CHAIN, STB_XKV_FP16)
-enum Option { OPT_XATTN_V2 = 0, OPT_DECODE_CHAIN, OPT_XKV_FP16, OPT_COUNT };
+// meaning so a whole process can be flipped without code (STB_DECODE_CHAIN)
+enum Option { OPT_DECODE_CHAIN = 0, OPT_COUNT };
 int option(Option o);
 
 template <typename... KArgs, typename... Args>

@@ -113,22 +113,32 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// cross-attention of one new token per sequence over the per-window K and V, head-major [B][H][T][64]: every
-// (sequence, head) is a set of contiguous streams.  HBM-bound, so the decode layout spends 3 bytes per element instead
-// of the 4 of the split-fp16 planes the GEMMs use:
-//     x ~= hi + q * s_row,   hi = fp16(x) (the GEMM plane itself), q = int8 residual (stored biased, u8 = q + 128),
-//     s_row = 2^(E-18) with E the exponent of the largest |hi| of the 64-element row (one float per key row)
-// |x - (hi + q s_row)| <= 2^-19 max|row|: 250x tighter than fp16 alone, ~8x looser than the hi+lo planes -- well inside
-// the parity gates (logits 1e-3; measured in tests/test_gpu_decode.py) -- for 2 x 1500 x (64 x 3 + 4) B = 588 KB per
-// (sequence, head) per step instead of 768 KB.  Single-plane precision (no lo planes) keeps plain fp16 K / V.
+// cross-attention of one new token per sequence over the per-window K and V, head-major fp16 [B][H][T][64]: every
+// (sequence, head) is a pair of contiguous 192 KB streams.  HBM-bound: 2 x 1500 x 128 B = 384 KB per (sequence, head) per
+// step.  The decode step reads the fp16 `hi` plane only -- K is the GEMM plane itself, V a head-major copy written once
+// per window batch.  Measured at 32 layers against the fp32 oracle (tests/test_gpu_depth.py): worst step-logit error
+// 2.15e-5 with fp16 K/V vs 2.07e-5 with the 3-byte hi + int8-residual format this kernel used before (gate 1e-3), greedy
+// tokens bit-exact -- the residual bought nothing measurable, so its 35 % of extra bytes were dropped.
 //
-// Flash-decoding layout: the keys of one (b,h) are cut into XS splits; one CTA (4 warps) streams its split ONCE,
-// reading K and V rows of the same key together (8 lanes per row, 4 keys per warp load, 4 keys in flight per lane
-// group), with an online softmax per lane group.  Each CTA writes (m, l, acc[64]); the last CTA of a (b,h) to finish
+// Flash-decoding layout: the keys of one (b,h) are cut into XS splits.  One CTA (4 warps) owns one split: an elected thread
+// issues the split's K and V as four 1-D bulk copies (cp.async.bulk, 12 KB each) into shared memory BEFORE waiting on the
+// producer of q (programmatic dependent launch: the K/V stream does not depend on it), so with 4 CTAs per SM ~190 KB per
+// SM are in flight and the copy engine, not registers, holds the memory-level parallelism.  8 lanes share a key row
+// (one 16-byte shared load of K and of V per lane), online softmax per lane group with ONE rescale per block of 4 keys,
+// the 16 lane groups merged through shared memory; each CTA writes (m, l, acc[64]) and the last CTA of a (b,h) to finish
 // (atomic ticket) merges the XS partials and writes the output.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int XS = 4;                       // key splits per (sequence, head)
-constexpr int XS_KEYS = 376;                // keys per split (multiple of 8; 4 x 376 >= 1500)
+constexpr int XS = 8;                       // key splits per (sequence, head)
+constexpr int XS_KEYS = 188;                // keys per split (8 x 188 = 1504 >= 1500)
+constexpr int XC = 2;                       // bulk-copy chunks per split (compute starts when the first one lands)
+constexpr int XC_KEYS = 94;
+constexpr int X_SMEM = XC * 2 * XC_KEYS * 128;   // K | V per chunk: 48128 B
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 __device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
     const __half2* h = reinterpret_cast<const __half2*>(&a);
@@ -140,161 +150,91 @@ __device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
     }
 }
 
-// u8 residuals (biased by 128) of 8 elements -> floats: 0x4B000000 | u is the float 8388608 + u
-__device__ __forceinline__ void unpack8q(const uint2& a, float (&f)[8]) {
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-        const uint32_t w = e < 4 ? a.x : a.y;
-        f[e] = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (uint32_t)(e & 3))) - 8388736.0f;
-    }
-}
-
-// biased u8 residuals of elements (k, k+1) of one 32-bit word -> half2 (r_k, r_k+1), exact: 0x6400 | u is the half 1024 + u
-__device__ __forceinline__ __half2 q8_pair(uint32_t w, int k) {
-    const uint32_t sel = k == 0 ? 0x4140u : 0x4342u;          // bytes [u_k, 0x64, u_k+1, 0x64]
-    const uint32_t bits = __byte_perm(w, 0x64646464u, sel);
-    return __hsub2(*reinterpret_cast<const __half2*>(&bits), __floats2half2_rn(1152.f, 1152.f));
-}
-
-// V2 (STB_XATTN_V2=1, not the default until it has run on hardware): (a) the residual part of q.k is a correction of
-// relative size <= 2^-11, so it is evaluated with packed half2 FMAs (its own 2^-11 rounding lands at 2^-22 of the score);
-// (b) the online-softmax rescale happens once per block of 4 keys instead of once per key.
-template <bool Q8, bool V2>
-__global__ void __launch_bounds__(128, 3)
-decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const uint8_t* __restrict__ k_q,
-                         const float* __restrict__ k_s, const __half* __restrict__ v_hi, const uint8_t* __restrict__ v_q,
-                         const float* __restrict__ v_s, int d, int T, float* __restrict__ partial,
-                         int* __restrict__ tickets, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                         float* __restrict__ out_f32) {
+__global__ void __launch_bounds__(128, 4)
+decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const __half* __restrict__ v_hi, int d,
+                         int T, float* __restrict__ partial, int* __restrict__ tickets, __half* __restrict__ out_hi,
+                         __half* __restrict__ out_lo, float* __restrict__ out_f32) {
+    extern __shared__ __align__(128) uint8_t x_smem[];       // [chunk][K rows | V rows][XC_KEYS][128 B]
+    __shared__ __align__(8) uint64_t s_bar[XC];
     __shared__ float s_m[4][4], s_l[4][4];
     __shared__ float s_acc[4][4][64];
     __shared__ int s_last;
     const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z, H = gridDim.y;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane & 7, grp = lane >> 3;
+    const int sub = lane & 7, grp = lane >> 3, g16 = w * 4 + grp;
     const int key0 = split * XS_KEYS, key1 = min(T, key0 + XS_KEYS);
+    const int nkeys = max(key1 - key0, 0);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < XC; ++c) mbar_init(&s_bar[c], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long row0 = ((long long)b * H + h) * T + key0;
+#pragma unroll
+        for (int c = 0; c < XC; ++c) {
+            const int n = min(max(nkeys - c * XC_KEYS, 0), XC_KEYS);
+            if (n > 0) {
+                const uint32_t bytes = (uint32_t)n * 128u;
+                uint8_t* dst = x_smem + (size_t)c * 2 * XC_KEYS * 128;
+                mbar_arrive_expect_tx(&s_bar[c], 2 * bytes);
+                bulk_load_1d(dst, k_hi + (row0 + c * XC_KEYS) * 64, bytes, &s_bar[c]);
+                bulk_load_1d(dst + XC_KEYS * 128, v_hi + (row0 + c * XC_KEYS) * 64, bytes, &s_bar[c]);
+            }
+        }
+    }
     pdl_trigger();
-    pdl_wait();                                              // q comes from the preceding GEMV
+    pdl_wait();                                              // q comes from the preceding linear
     float qr[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e] * 0.125f;
-    const long long rowbase = ((long long)b * H + h) * T;
-    const long long base = rowbase * 64 + sub * 8;
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    __half2 qh[4];                                           // V2: the (scaled) query in fp16 for the residual term
 #pragma unroll
-    for (int i = 0; i < 4; ++i) qh[i] = __floats2half2_rn(qr[2 * i], qr[2 * i + 1]);
-    // this lane group's keys: key0 + w*4 + grp + 16*i
-    for (int j0 = key0 + w * 4 + grp; j0 < key1 + 48; j0 += 64) {          // warp-uniform trip count
-        uint4 kh[4], vh[4];
-        uint2 kq[4], vq[4];
-        float ks[4], vs[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u * 16;
-            kh[u] = vh[u] = make_uint4(0, 0, 0, 0);
-            kq[u] = vq[u] = make_uint2(0x80808080u, 0x80808080u);
-            ks[u] = vs[u] = 0.f;
-            if (j < key1) {
-                const long long off = base + (long long)j * 64;
-                kh[u] = __ldg(reinterpret_cast<const uint4*>(k_hi + off));
-                vh[u] = __ldg(reinterpret_cast<const uint4*>(v_hi + off));
-                if (Q8) {
-                    kq[u] = __ldg(reinterpret_cast<const uint2*>(k_q + off));
-                    vq[u] = __ldg(reinterpret_cast<const uint2*>(v_q + off));
-                    ks[u] = __ldg(k_s + rowbase + j);
-                    vs[u] = __ldg(v_s + rowbase + j);
-                }
-            }
-        }
-        if (V2) {
+    for (int c = 0; c < XC; ++c) {
+        const int n = min(max(nkeys - c * XC_KEYS, 0), XC_KEYS);
+        if (n <= 0) break;
+        mbar_wait(&s_bar[c], 0, 40 + c);
+        const uint8_t* kc = x_smem + (size_t)c * 2 * XC_KEYS * 128 + sub * 16;
+        const uint8_t* vc = kc + XC_KEYS * 128;
+        // this lane group's keys of the chunk: g16 + 16 i; four at a time
+        for (int j0 = g16; j0 < n; j0 += 64) {
             float sc[4];
+            uint4 vh[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u * 16;
+                const bool ok = j < n;                        // uniform within the 8-lane group
+                const uint4 kh = ok ? *reinterpret_cast<const uint4*>(kc + j * 128) : make_uint4(0, 0, 0, 0);
+                vh[u] = ok ? *reinterpret_cast<const uint4*>(vc + j * 128) : make_uint4(0, 0, 0, 0);
                 float kf[8];
-                unpack8(kh[u], kf);
+                unpack8(kh, kf);
                 float s = 0.f;
 #pragma unroll
                 for (int e = 0; e < 8; ++e) s = fmaf(qr[e], kf[e], s);
-                if (Q8) {
-                    __half2 a2 = __floats2half2_rn(0.f, 0.f);
-                    a2 = __hfma2(qh[0], q8_pair(kq[u].x, 0), a2);
-                    a2 = __hfma2(qh[1], q8_pair(kq[u].x, 2), a2);
-                    a2 = __hfma2(qh[2], q8_pair(kq[u].y, 0), a2);
-                    a2 = __hfma2(qh[3], q8_pair(kq[u].y, 2), a2);
-                    const float2 f2 = __half22float2(a2);
-                    s = fmaf(f2.x + f2.y, ks[u], s);
-                }
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
                 s += __shfl_xor_sync(0xffffffffu, s, 4);
-                sc[u] = (j0 + u * 16 < key1) ? s : -INFINITY;
+                sc[u] = ok ? s : -INFINITY;
             }
-            if (j0 < key1) {                                  // uniform within the 8-lane group; key u = 0 is valid
-                const float mn = fmaxf(fmaxf(m, sc[0]), fmaxf(fmaxf(sc[1], sc[2]), sc[3]));
-                const float corr = expf(m - mn);              // exp(-inf) = 0 for the first block
-                l *= corr;
+            const float mn = fmaxf(fmaxf(m, sc[0]), fmaxf(fmaxf(sc[1], sc[2]), sc[3]));   // key u = 0 is valid: finite
+            const float corr = expf(m - mn);                  // exp(-inf) = 0 for the first block
+            l *= corr;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] *= corr;
+            for (int e = 0; e < 8; ++e) acc[e] *= corr;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float p = expf(sc[u] - mn);         // 0 for keys past the split
-                    float vf[8], t[8];
-                    unpack8(vh[u], vf);
-                    l += p;
-                    if (Q8) {
-                        unpack8q(vq[u], t);
-                        const float p2 = p * vs[u];
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], fmaf(p2, t[e], acc[e]));
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
-                    }
-                }
-                m = mn;
-            }
-        } else {
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int j = j0 + u * 16;
-            float kf[8], t[8];
-            unpack8(kh[u], kf);
-            float s = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) s = fmaf(qr[e], kf[e], s);
-            if (Q8) {                                         // q . (hi + r s_row) = q . hi + s_row (q . r)
-                unpack8q(kq[u], t);
-                float sr = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) sr = fmaf(qr[e], t[e], sr);
-                s = fmaf(sr, ks[u], s);
-            }
-            s += __shfl_xor_sync(0xffffffffu, s, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4);
-            if (j < key1) {                                   // uniform within the 8-lane group
-                const float mn = fmaxf(m, s);
-                const float corr = expf(m - mn);              // exp(-inf) = 0 on the first key
-                const float p = expf(s - mn);
+            for (int u = 0; u < 4; ++u) {
+                const float p = expf(sc[u] - mn);             // 0 for keys past the chunk
                 float vf[8];
                 unpack8(vh[u], vf);
-                l = l * corr + p;
-                if (Q8) {                                     // acc += p hi + (p s_row) r
-                    unpack8q(vq[u], t);
-                    const float p2 = p * vs[u];
+                l += p;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], fmaf(p2, t[e], acc[e] * corr));
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e] * corr);
-                }
-                m = mn;
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
             }
+            m = mn;
         }
-        }   // !V2
     }
     // ---- combine the 16 lane groups of the CTA ----
     if (sub == 0) { s_m[w][grp] = m; s_l[w][grp] = l; }
@@ -351,66 +291,22 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
     }
 }
 
-// int8 residual of a 64-element row held two elements per lane: hi = fp16 plane values, lo = fp16 residual plane values.
-// Returns the biased bytes (q + 128) of this lane's two elements and the row scale s_row = 2^(E - 18).
-__device__ __forceinline__ void q8_row(float hi0, float hi1, float lo0, float lo1, uint8_t& u0, uint8_t& u1, float& scale) {
-    uint32_t eb = max(__float_as_uint(hi0) & 0x7f800000u, __float_as_uint(hi1) & 0x7f800000u);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) eb = max(eb, __shfl_xor_sync(0xffffffffu, eb, o));
-    eb = max(eb, 113u << 23);                                // fp16 subnormal rows: E = -14
-    scale = __uint_as_float(eb - (18u << 23));               // 2^(E - 18); |lo| <= 2^(E - 11) -> |q| <= 128
-    const float inv = __uint_as_float((254u << 23) - (eb - (18u << 23)));   // 1 / scale, exact (power of two)
-    const int q0 = max(-127, min(127, __float2int_rn(lo0 * inv)));
-    const int q1 = max(-127, min(127, __float2int_rn(lo1 * inv)));
-    u0 = (uint8_t)(q0 + 128);
-    u1 = (uint8_t)(q1 + 128);
-}
-
-// K head-major split planes [rows][64] -> int8 residual plane + row scales (one warp per row).
-__global__ void __launch_bounds__(256) pack_q8_rows_kernel(const __half* __restrict__ hi, const __half* __restrict__ lo,
-                                                           long long rows, uint8_t* __restrict__ q, float* __restrict__ scale) {
-    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
-    const float2 h = __half22float2(reinterpret_cast<const __half2*>(hi + row * 64)[lane]);
-    const float2 l = __half22float2(reinterpret_cast<const __half2*>(lo + row * 64)[lane]);
-    uint8_t u0, u1;
-    float sc;
-    q8_row(h.x, h.y, l.x, l.y, u0, u1, sc);
-    reinterpret_cast<uint16_t*>(q + row * 64)[lane] = (uint16_t)u0 | ((uint16_t)u1 << 8);
-    if (lane == 0) scale[row] = sc;
-}
-
-// V^T split [B][H][64][Tp] -> V head-major [B][H][T][64] (decode-step layout): fp16 hi plane, and -- when the lo plane
-// is given -- its int8 residual plane + row scales.  64 x 64 smem tile transpose.
-__global__ void __launch_bounds__(256) v_headmajor_kernel(const __half* __restrict__ vT_hi, const __half* __restrict__ vT_lo,
-                                                          int T, int Tp, __half* __restrict__ v_hi, uint8_t* __restrict__ v_q,
-                                                          float* __restrict__ v_s) {
-    __shared__ __half tile[2][64][72];
+// V^T plane [B][H][64][Tp] fp16 -> V head-major [B][H][T][64] (decode-step layout).  64 x 64 smem tile transpose.
+__global__ void __launch_bounds__(256) v_headmajor_kernel(const __half* __restrict__ vT_hi, int T, int Tp,
+                                                          __half* __restrict__ v_hi) {
+    __shared__ __half tile[64][72];
     const long long bh = blockIdx.y;
     const int t0 = blockIdx.x * 64;
-    const bool q8 = vT_lo != nullptr;
     for (int i = threadIdx.x; i < 64 * 64; i += 256) {
         const int c = i >> 6, t = i & 63;
-        const bool ok = t0 + t < T;
-        tile[0][c][t] = ok ? vT_hi[(bh * 64 + c) * Tp + t0 + t] : __float2half(0.f);
-        if (q8) tile[1][c][t] = ok ? vT_lo[(bh * 64 + c) * Tp + t0 + t] : __float2half(0.f);
+        tile[c][t] = (t0 + t < T) ? vT_hi[(bh * 64 + c) * Tp + t0 + t] : __float2half(0.f);
     }
     __syncthreads();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int t = w; t < 64; t += 8) {                        // one warp per key row, two channels per lane
         if (t0 + t >= T) break;
         const long long row = bh * T + t0 + t;
-        const __half h0 = tile[0][2 * lane][t], h1 = tile[0][2 * lane + 1][t];
-        reinterpret_cast<__half2*>(v_hi + row * 64)[lane] = __halves2half2(h0, h1);
-        if (q8) {
-            uint8_t u0, u1;
-            float sc;
-            q8_row(__half2float(h0), __half2float(h1), __half2float(tile[1][2 * lane][t]), __half2float(tile[1][2 * lane + 1][t]),
-                   u0, u1, sc);
-            reinterpret_cast<uint16_t*>(v_q + row * 64)[lane] = (uint16_t)u0 | ((uint16_t)u1 << 8);
-            if (lane == 0) v_s[row] = sc;
-        }
+        reinterpret_cast<__half2*>(v_hi + row * 64)[lane] = __halves2half2(tile[2 * lane][t], tile[2 * lane + 1][t]);
     }
 }
 
@@ -459,7 +355,7 @@ __device__ __forceinline__ float block_sum(float v, BlockRed& r) {
 __global__ void __launch_bounds__(1024)
 sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, int ts_begin, int no_timestamps,
                      const uint8_t* __restrict__ suppress, const uint8_t* __restrict__ first_mask,
-                     const uint8_t* __restrict__ ts_mask, int max_initial_ts, int apply_ts_rules,
+                     const uint8_t* __restrict__ ts_mask, long long ts_mask_stride, int max_initial_ts, int apply_ts_rules,
                      const int32_t* __restrict__ forced_table, stb_seq_state* __restrict__ states,
                      int32_t* __restrict__ next_out, int32_t* __restrict__ token_table, int32_t* __restrict__ argmax_table,
                      int table_rows) {
@@ -468,6 +364,7 @@ sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, i
     pdl_trigger();
     pdl_wait();
     float* l = logits + (long long)b * ld;
+    if (ts_mask) ts_mask += (long long)b * ts_mask_stride;   // stride 0: one mask for the batch; else one row per sequence
     stb_seq_state st = states[b];
     const bool first = st.n_sampled == 0;
     const bool last_ts = st.n_sampled >= 1 && st.last_tok >= ts_begin;
@@ -543,8 +440,10 @@ sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, i
         const int B = gridDim.x;
         const bool in_table = st.n_sampled < table_rows;
         if (argmax_table && in_table) argmax_table[(long long)st.n_sampled * B + b] = a;
+        // GreedyDecoder.update accumulates the log-prob of ITS pick (the argmax); a forced script (benchmarks, tests) only
+        // replaces the token that is appended afterwards, exactly as oracle/stable_path.py:decode_window does
+        const float lp = (l[a] - gmax) - log_s;
         if (forced_table && in_table) next = forced_table[(long long)st.n_sampled * B + b];
-        const float lp = (l[next] - gmax) - log_s;
         if (!was_done) st.sum_logprob += lp;
         if (was_done) next = eot;                           // finished rows keep emitting EOT
         if (token_table && in_table) token_table[(long long)st.n_sampled * B + b] = next;
@@ -568,12 +467,13 @@ __global__ void bump_pos_kernel(int32_t* pos) {
 
 extern "C" int stb_sample_greedy(float* logits, long long ld, int B, int V, int eot, int ts_begin, int no_timestamps,
                                  const uint8_t* suppress_mask, const uint8_t* first_step_mask, const uint8_t* ts_mask,
-                                 int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
+                                 long long ts_mask_stride, int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
                                  int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows, void* stream) {
     STB_REQUIRE(logits && states && next_out && B >= 1 && V >= 1 && ld >= V, "stb_sample_greedy: bad arguments");
+    STB_REQUIRE(ts_mask_stride == 0 || ts_mask_stride >= 1501, "stb_sample_greedy: ts_mask_stride must be 0 (shared) or >= 1501");
     stb::ProfScope ps("sample_greedy", (cudaStream_t)stream, (double)B * V * 4.0 * 3);
     STB_CUDA_OK(stb::launch_pdl(stb::sample_greedy_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, logits, ld, V, eot, ts_begin,
-                                no_timestamps, suppress_mask, first_step_mask, ts_mask, max_initial_ts, apply_ts_rules, forced_table,
+                                no_timestamps, suppress_mask, first_step_mask, ts_mask, ts_mask_stride, max_initial_ts, apply_ts_rules, forced_table,
                                 states, next_out, token_table, argmax_table, table_rows));
     STB_LAUNCH_OK();
     return STB_OK;
@@ -589,31 +489,25 @@ int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d
 }
 int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
                       __half* ol, float* of, cudaStream_t st) {
-    const bool q8 = kv.k_q != nullptr;
-    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * (q8 ? 64 * 3.0 + 4.0 : 64 * 2.0));
-    const bool v2 = option(OPT_XATTN_V2) != 0;
-#define STB_XATTN(Q, V)                                                                                                     \
-    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<Q, V>, dim3(XS, H, B), dim3(128), 0, st, q, kv.k_hi, kv.k_q, kv.k_s, kv.v_hi, \
-                           kv.v_q, kv.v_s, d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of))
-    if (q8 && v2) STB_XATTN(true, true);
-    else if (q8) STB_XATTN(true, false);
-    else if (v2) STB_XATTN(false, true);
-    else STB_XATTN(false, false);
-#undef STB_XATTN
+    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0);
+    static bool attr_set[64] = {};                          // per device ordinal
+    int dev = 0;
+    STB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM));
+        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set[dev] = true;
+    }
+    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel, dim3(XS, H, B), dim3(128), (size_t)X_SMEM, st, q, kv.k_hi, kv.v_hi, d,
+                           (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
     STB_LAUNCH_OK();
     return STB_OK;
 }
 size_t decode_cross_scratch_bytes(int B, int H) { return (size_t)B * H * XS * 66 * sizeof(float) + (size_t)B * H * sizeof(int) + 256; }
-int v_headmajor(const __half* vT_hi, const __half* vT_lo, int BH, int T, int Tp, __half* v_hi, uint8_t* v_q, float* v_s,
-                cudaStream_t st) {
-    ProfScope ps("v_headmajor", st, (double)BH * T * 64 * (vT_lo ? 4.0 + 3.0 : 4.0));
-    v_headmajor_kernel<<<dim3(cdiv(T, 64), BH), 256, 0, st>>>(vT_hi, vT_lo, T, Tp, v_hi, v_q, v_s);
-    STB_LAUNCH_OK();
-    return STB_OK;
-}
-int pack_q8_rows(const __half* hi, const __half* lo, long long rows, uint8_t* q, float* scale, cudaStream_t st) {
-    ProfScope ps("pack_q8_rows", st, (double)rows * 64 * 5.0);
-    pack_q8_rows_kernel<<<(unsigned)cdiv(rows, 8), 256, 0, st>>>(hi, lo, rows, q, scale);
+int decode_cross_splits() { return XS; }
+int v_headmajor(const __half* vT_hi, int BH, int T, int Tp, __half* v_hi, cudaStream_t st) {
+    ProfScope ps("v_headmajor", st, (double)BH * T * 64 * 4.0);
+    v_headmajor_kernel<<<dim3(cdiv(T, 64), BH), 256, 0, st>>>(vT_hi, T, Tp, v_hi);
     STB_LAUNCH_OK();
     return STB_OK;
 }

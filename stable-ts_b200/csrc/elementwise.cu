@@ -302,7 +302,46 @@ __global__ void __launch_bounds__(512) token_prob_kernel(const float* __restrict
     }
 }
 
+// Full probability rows (the 3-D form of the refine plugin, stable_whisper/alignment.py:669-671): out[r][c] =
+// softmax(logits[r][:n_classes])[c].  One CTA per row; the row (200 KB) is re-read from L2 for the second and third pass.
+__global__ void __launch_bounds__(512) softmax_probs_kernel(const float* __restrict__ logits, long long ld, int n_classes,
+                                                            float* __restrict__ out, long long ld_out) {
+    __shared__ float red[16];
+    const int r = blockIdx.x;
+    const float* l = logits + (long long)r * ld;
+    float* o = out + (long long)r * ld_out;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n_classes; i += blockDim.x) mx = fmaxf(mx, l[i]);
+    mx = warp_max(mx);
+    if (lane == 0) red[w] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int i = 1; i < 16; ++i) mx = fmaxf(mx, red[i]);
+    __syncthreads();
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n_classes; i += blockDim.x) s += expf(l[i] - mx);
+    s = warp_sum(s);
+    if (lane == 0) red[w] = s;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tot += red[i];
+    for (int i = threadIdx.x; i < n_classes; i += blockDim.x) o[i] = expf(l[i] - mx) / tot;
+}
+
 }  // namespace stb
+
+extern "C" int stb_softmax_probs(const float* logits, long long ld, int n_rows, int n_classes, float* out, long long ld_out,
+                                 void* stream) {
+    STB_REQUIRE(logits && out && n_classes > 0 && ld >= n_classes && ld_out >= n_classes, "stb_softmax_probs: bad arguments");
+    if (n_rows == 0) return STB_OK;
+    stb::ProfScope ps("softmax_probs", (cudaStream_t)stream, (double)n_rows * n_classes * 8.0);
+    stb::softmax_probs_kernel<<<n_rows, 512, 0, (cudaStream_t)stream>>>(logits, ld, n_classes, out, ld_out);
+    STB_LAUNCH_OK();
+    return STB_OK;
+}
 
 extern "C" int stb_token_probs(const float* logits, long long ld, int n_rows, int n_classes, const int32_t* targets,
                                float* prob_out, int32_t* rank_out, void* stream) {

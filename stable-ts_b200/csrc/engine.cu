@@ -231,19 +231,15 @@ static int encoder_forward(stb_model* m, const float* mel, int B, float* xa_f32,
 // ---------------------------------------------------------------------------------------------------------
 // cross K / V^T for all decoder layers
 // ---------------------------------------------------------------------------------------------------------
-struct CrossKV {             // per layer: K split head-major [B][H][T][64], vT split [B][H][64][Tp], V split head-major
+struct CrossKV {             // per layer: K split head-major [B][H][T][64], vT split [B][H][64][Tp], V hi head-major
     size_t k_elems, v_elems, layer_halfs;
-    size_t rows;              // B * H * T key rows (one scale each in the decode-step format)
 };
 static CrossKV cross_layout(const stb_model* m, int B) {
     CrossKV c;
     c.k_elems = (size_t)B * m->dims.n_audio_ctx * m->dims.n_text_state;
     c.v_elems = (size_t)B * m->dims.n_text_state * STB_KPAD;
-    // per layer: K hi | K lo | V^T hi | V^T lo | decode-step region of 2 * k_elems halfs + 4 * rows halfs:
-    //   V head-major hi (k_elems halfs) | K residual u8 (k_elems bytes) | V residual u8 (k_elems bytes) |
-    //   K row scales (rows floats) | V row scales (rows floats),      rows = B * H * T  (decode.cu, 3-byte format)
-    c.rows = (size_t)B * m->dims.n_text_head * m->dims.n_audio_ctx;
-    c.layer_halfs = 2 * (2 * c.k_elems + c.v_elems) + 4 * c.rows;
+    // per layer: K hi | K lo | V^T hi | V^T lo | V hi head-major (k_elems halfs; the decode step's fp16 V, decode.cu)
+    c.layer_halfs = 2 * (2 * c.k_elems + c.v_elems) + c.k_elems;
     return c;
 }
 static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split& K, Split& vT, CrossDecodeKV* Vd = nullptr) {
@@ -253,16 +249,8 @@ static void cross_ptrs(const stb_model* m, int B, const void* base, int l, Split
     K.hi = p; K.lo = lo ? p + c.k_elems : nullptr;
     vT.hi = p + 2 * c.k_elems; vT.lo = lo ? p + 2 * c.k_elems + c.v_elems : nullptr;
     if (Vd) {
-        __half* v = p + 2 * c.k_elems + 2 * c.v_elems;
-        uint8_t* q = reinterpret_cast<uint8_t*>(v + c.k_elems);
-        float* sc = reinterpret_cast<float*>(q + 2 * c.k_elems);
         Vd->k_hi = K.hi;
-        Vd->v_hi = v;
-        const bool q8 = lo && option(OPT_XKV_FP16) == 0;     // xkv_fp16: the step reads only the fp16 planes (A/B knob)
-        Vd->k_q = q8 ? q : nullptr;
-        Vd->v_q = q8 ? q + c.k_elems : nullptr;
-        Vd->k_s = q8 ? sc : nullptr;
-        Vd->v_s = q8 ? sc + c.rows : nullptr;
+        Vd->v_hi = p + 2 * c.k_elems + 2 * c.v_elems;
     }
 }
 
@@ -286,13 +274,8 @@ static int cross_kv(stb_model* m, const __half* xa_hi, const __half* xa_lo, int 
         }
         STB_TRY(project_vT(m, xa, B, T, d, offs(W_HI(L, STB_L_CKV_W), (long long)d * d), offs(W_LO(L, STB_L_CKV_W), (long long)d * d),
                            W_F32(L, STB_L_CKV_B) + d, vT, STB_KPAD, st));
-        if (decode_layout) {   // head-major copy of V for the decode-step kernel (contiguous per (sequence, head), like K)
-            STB_TRY(v_headmajor(vT.hi, Vd.v_q ? vT.lo : nullptr, B * D.n_text_head, T, STB_KPAD, const_cast<__half*>(Vd.v_hi),
-                                const_cast<uint8_t*>(Vd.v_q), const_cast<float*>(Vd.v_s), st));
-            if (K.lo && Vd.k_q)   // 3-byte decode format of K: int8 residual + row scale next to the fp16 hi plane
-                STB_TRY(pack_q8_rows(K.hi, K.lo, (long long)B * D.n_text_head * T, const_cast<uint8_t*>(Vd.k_q),
-                                     const_cast<float*>(Vd.k_s), st));
-        }
+        if (decode_layout)     // head-major fp16 copy of V for the decode-step kernel (contiguous per (sequence, head), like K)
+            STB_TRY(v_headmajor(vT.hi, B * D.n_text_head, T, STB_KPAD, const_cast<__half*>(Vd.v_hi), st));
     }
     return STB_OK;
 }
@@ -446,7 +429,7 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.x = c.take<float>((size_t)B * d);
     w.qkv = c.take<float>((size_t)B * 3 * d);
     w.q = c.take<float>((size_t)B * d);
-    w.xpart = c.take<float>((size_t)B * m->dims.n_text_head * 4 * 66);
+    w.xpart = c.take<float>((size_t)B * m->dims.n_text_head * decode_cross_splits() * 66);
     w.tickets = c.take<int>((size_t)B * m->dims.n_text_head);
     w.ln = take_split(c, (size_t)B * d, lo);
     w.attn = take_split(c, (size_t)B * d, lo);

@@ -37,22 +37,16 @@ int capture_heads(const float* S, int B, int H, int M, long long ld, float* out,
 
 int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
                      __half* ol, float* of, cudaStream_t st);
-// decode-step view of one layer's cross K / V (head-major [B][H][T][64]): fp16 hi planes + int8 residuals (biased u8)
-// + one scale per key row; k_q == nullptr: single-plane precision (plain fp16)
+// decode-step view of one layer's cross K / V: fp16 planes, head-major [B][H][T][64] (K is the GEMM hi plane itself)
 struct CrossDecodeKV {
     const __half* k_hi;
-    const uint8_t* k_q;
-    const float* k_s;
     const __half* v_hi;
-    const uint8_t* v_q;
-    const float* v_s;
 };
 int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
                       __half* ol, float* of, cudaStream_t st);
 size_t decode_cross_scratch_bytes(int B, int H);
-int v_headmajor(const __half* vT_hi, const __half* vT_lo, int BH, int T, int Tp, __half* v_hi, uint8_t* v_q, float* v_s,
-                cudaStream_t st);
-int pack_q8_rows(const __half* hi, const __half* lo, long long rows, uint8_t* q, float* scale, cudaStream_t st);
+int decode_cross_splits();
+int v_headmajor(const __half* vT_hi, int BH, int T, int Tp, __half* v_hi, cudaStream_t st);
 int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, const void* w_lo, int N, const float* bias,
          int act, const float* res, long long ld_res, float* out_f32, void* out_hi, void* out_lo, long long ld_out,
          cudaStream_t st);

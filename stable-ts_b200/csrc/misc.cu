@@ -57,9 +57,7 @@ bool pdl_enabled() {
 
 struct OptDef { const char* name; const char* env; int dflt; };
 static const OptDef g_opt_defs[OPT_COUNT] = {
-    {"xattn_v2", "STB_XATTN_V2", 0},          // decode cross-attention: half2 residual dot + block-wise rescale
     {"decode_chain", "STB_DECODE_CHAIN", 0},  // decode linears between two attention kernels as one persistent kernel
-    {"xkv_fp16", "STB_XKV_FP16", 0},          // decode cross-attention reads only the fp16 plane of K / V (2 B/element)
 };
 static int g_opt[OPT_COUNT];
 static bool g_opt_init = false;

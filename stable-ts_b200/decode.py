@@ -104,19 +104,28 @@ class StepEngine:
         m = self.m
         L.check(m._lib.stb_sample_greedy(L.ptr(self.logits), self.ldv, self.B, m.dims.n_vocab, int(tk.eot),
                                          int(tk.timestamp_begin), int(tk.no_timestamps), L.ptr(suppress), L.ptr(first_mask),
-                                         L.ptr(ts_mask), int(max_initial_ts), int(apply_ts_rules), L.ptr(self.forced),
+                                         L.ptr(ts_mask), 0 if ts_mask is None or ts_mask.ndim == 1 else int(ts_mask.stride(0)),
+                                         int(max_initial_ts), int(apply_ts_rules), L.ptr(self.forced),
                                          L.ptr(self.seq), L.ptr(self.next), L.ptr(self.tok_table), L.ptr(self.arg_table),
                                          self.rows, L.stream_ptr()))
 
 
+def decode_windows(model: B200Whisper, *args, **kwargs):
+    """See ``_decode_windows``; runs with the model's device current (launches go to that device's current stream)."""
+    with torch.cuda.device(model.device):
+        return _decode_windows(model, *args, **kwargs)
+
+
 @torch.no_grad()
-def decode_windows(model: B200Whisper, tokenizer, enc: dict, options: Optional[DecodingOptions] = None, *,
+def _decode_windows(model: B200Whisper, tokenizer, enc: dict, options: Optional[DecodingOptions] = None, *,
                    ts_token_mask: Optional[torch.Tensor] = None, forced_tokens: Optional[torch.Tensor] = None,
                    use_graph: bool = True, poll_every: int = 16, return_step_logits: bool = False, ckv=None,
                    reuse_buffers: bool = False):
     """Greedy (temperature 0) decode of the B windows whose encoder output is ``enc`` (from ``model.encode``).
 
-    ts_token_mask: bool [1501] shared by the batch (silent-timestamp suppression, decode.py:14-16) or None.
+    ts_token_mask: silent-timestamp suppression (decode.py:14-16): bool [1501] shared by the batch, bool [B, 1501] with one
+                   row per window (what the reference computes, original_whisper.py:504-511), a list of B optional [1501]
+                   masks (None = nothing suppressed for that window), or None.
     forced_tokens: int [steps, B] -- the token appended at each step instead of the argmax (fixed-length scripts for
                    random-weight benchmarks); the argmax of every step is still returned.
     reuse_buffers: keep the cross K/V block, the KV cache and the step workspace in model-owned buffers (the returned
@@ -145,7 +154,21 @@ def decode_windows(model: B200Whisper, tokenizer, enc: dict, options: Optional[D
     if options.suppress_blank:
         first[tokenizer.encode(" ") + [tokenizer.eot]] = 1
     sup, first = sup.to(dev), first.to(dev)
-    tsm = None if ts_token_mask is None else ts_token_mask.to(torch.uint8).to(dev).contiguous()
+    tsm = None
+    if ts_token_mask is not None:
+        if isinstance(ts_token_mask, (list, tuple)):
+            if len(ts_token_mask) != B:
+                raise ValueError(f"ts_token_mask: {len(ts_token_mask)} masks for {B} windows")
+            rows = torch.zeros(B, 1501, dtype=torch.uint8)
+            for i, mk in enumerate(ts_token_mask):
+                if mk is not None:
+                    rows[i] = torch.as_tensor(mk).to(torch.uint8)
+            ts_token_mask = rows
+        if ts_token_mask.ndim == 2 and ts_token_mask.shape[0] != B:
+            raise ValueError(f"ts_token_mask: {ts_token_mask.shape[0]} rows for {B} windows")
+        if ts_token_mask.shape[-1] != 1501:
+            raise ValueError("ts_token_mask must have 1501 entries per window")
+        tsm = ts_token_mask.to(torch.uint8).to(dev).contiguous()
     apply_rules = not options.without_timestamps
     max_init = -1
     if apply_rules and options.max_initial_timestamp:

@@ -18,7 +18,20 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 import torch
 
+import functools
+
 from . import _lib as L
+from .shim import WhisperProtocol
+
+
+def _on_device(fn):
+    """Run a kernel-launching method with the model's device current: the launches go to torch's current stream OF THAT
+    DEVICE (a model on cuda:1 must not enqueue on cuda:0's stream when the caller's current device differs)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **k):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **k)
+    return wrapped
 
 
 @dataclass
@@ -63,8 +76,10 @@ def mel_filterbank(n_mels: int) -> np.ndarray:
     return w.astype(np.float32)
 
 
-class B200Whisper:
-    """Whisper weights on one B200 + the kernel entry points.  ``precision``: "fp16x3" (parity mode) or "fp16"."""
+class B200Whisper(WhisperProtocol):
+    """Whisper weights on one B200 + the kernel entry points.  ``precision``: "fp16x3" (parity mode) or "fp16".
+    ``WhisperProtocol`` (shim.py) adds the whisper model-object surface (``encoder`` / ``decoder`` / hooks / kv-cache
+    protocol / ``detect_language``) that the unmodified reference code drives."""
 
     def __init__(self, dims, state_dict: Dict[str, torch.Tensor], device: Union[str, torch.device] = "cuda",
                  precision: str = "fp16x3", alignment_heads: Optional[Sequence[Tuple[int, int]]] = None):
@@ -87,9 +102,21 @@ class B200Whisper:
             alignment_heads = [(l, hh) for l in range(self.dims.n_text_layer // 2, self.dims.n_text_layer)
                                for hh in range(self.dims.n_text_head)]
         self.alignment_head_pairs = [(int(a), int(b)) for a, b in alignment_heads]
+        self.missing_alignment_heads = False
+        self.random_init = False
         with torch.cuda.device(self.device):
             self._pack(state_dict)
             self._frontend_tables()
+        self._init_protocol()
+
+    def set_alignment_heads(self, pairs_or_mask):
+        """(layer, head) pairs or a bool [n_text_layer, n_text_head] mask (whisper's ``set_alignment_heads`` takes the
+        base85 dump of such a mask)."""
+        if torch.is_tensor(pairs_or_mask) or isinstance(pairs_or_mask, np.ndarray):
+            m = torch.as_tensor(pairs_or_mask).to_dense() if getattr(pairs_or_mask, "is_sparse", False) else torch.as_tensor(pairs_or_mask)
+            pairs_or_mask = m.nonzero().tolist()
+        self.alignment_head_pairs = [(int(a), int(b)) for a, b in pairs_or_mask]
+        self.missing_alignment_heads = False
 
     # ---- reference model-protocol bits ----
     @property
@@ -204,6 +231,7 @@ class B200Whisper:
         return t
 
     # ---- a1 ----
+    @_on_device
     def log_mel(self, audio: torch.Tensor, padded_samples: Optional[int] = None, batch_global_max: bool = False
                 ) -> torch.Tensor:
         """audio fp32 [B, n] (device) -> mel fp32 [B, n_mels, 3000].  padded_samples=None pads to 30 s (align path)."""
@@ -222,6 +250,7 @@ class B200Whisper:
         return mel
 
     # ---- a2 ----
+    @_on_device
     def encode(self, mel: torch.Tensor) -> Dict[str, torch.Tensor]:
         """mel fp32 [B, n_mels, 3000] -> {"f32": [B,1500,d], "hi": fp16 [B*1500,d], "lo": ...}."""
         if mel.ndim == 2:
@@ -237,6 +266,7 @@ class B200Whisper:
                                               L.stream_ptr()))
         return {"f32": xa, "hi": hi, "lo": lo, "B": B}
 
+    @_on_device
     def cross_kv(self, enc: Dict[str, torch.Tensor], decode: bool = False, reuse: bool = False) -> torch.Tensor:
         """Cross-attention K / V^T of every decoder layer; ``decode=True`` also lays V out for the KV-cached decode step.
         ``reuse=True`` writes into a buffer owned by the model (overwritten by the next such call): a batch of 120
@@ -248,6 +278,7 @@ class B200Whisper:
         return out
 
     # ---- a3 ----
+    @_on_device
     def decode_forced(self, tokens: torch.Tensor, ckv: torch.Tensor, want_logits: bool = True,
                       heads: Union[None, str, Sequence[Tuple[int, int]]] = None, reuse: bool = False):
         """tokens int [B, M] -> (logits fp32 [B, M, V] view or None, qk fp32 [B, n_sel, M, 1504] or None).
@@ -282,6 +313,7 @@ class B200Whisper:
         return lv, qk
 
     # ---- a4 / a10 ----
+    @_on_device
     def token_probs(self, logits_rows: torch.Tensor, n_classes: int, targets: torch.Tensor, want_rank: bool = False):
         """logits_rows fp32 [n, >=n_classes] (row-strided view ok) -> (prob fp32 [n], rank int32 [n] | None)."""
         assert logits_rows.stride(-1) == 1
@@ -293,7 +325,18 @@ class B200Whisper:
                                           L.ptr(prob), L.ptr(rank), L.stream_ptr()))
         return prob, rank
 
+    @_on_device
+    def softmax_probs(self, logits_rows: torch.Tensor, n_classes: int) -> torch.Tensor:
+        """logits_rows fp32 [n, >=n_classes] (row-strided view ok) -> probabilities fp32 [n, n_classes] (device)."""
+        assert logits_rows.stride(-1) == 1
+        n = logits_rows.shape[0]
+        out = torch.empty(n, int(n_classes), dtype=torch.float32, device=self.device)
+        L.check(self._lib.stb_softmax_probs(L.ptr(logits_rows), logits_rows.stride(0), n, int(n_classes), L.ptr(out),
+                                            int(n_classes), L.stream_ptr()))
+        return out
+
     # ---- a5 ----
+    @_on_device
     def qk_postprocess(self, qk: torch.Tensor, S: int, F: int, R: Optional[int] = None, qk_scale: float = 1.0,
                        medfilt_width: int = 7) -> torch.Tensor:
         """qk fp32 [B, A, M, ld] -> matrix fp32 [B, R, F]; R defaults to M-1-S (the reference's [S:-1] slice)."""
@@ -307,6 +350,7 @@ class B200Whisper:
                                              ldm, L.ptr(ws), ws.numel(), L.stream_ptr()))
         return out[:, :, :F]
 
+    @_on_device
     def qk_postprocess_dynamic(self, qk_all: torch.Tensor, S: int, F: int, R: Optional[int] = None, count: int = 6,
                                prev_jumps: Optional[torch.Tensor] = None, reuse_softmax: bool = False,
                                qk_scale: float = 1.0, medfilt_width: int = 7) -> torch.Tensor:
@@ -323,6 +367,7 @@ class B200Whisper:
                                                      ws.numel(), L.stream_ptr()))
         return out[:, :, :F]
 
+    @_on_device
     def qk_postprocess_new(self, qk_all: torch.Tensor, S: int, F: int, R: Optional[int] = None, topk: int = 20,
                            w_colnorm: float = 1.0, w_rownorm: float = 1.0, w_coverage: float = 0.0, qk_scale: float = 1.0,
                            medfilt_width: int = 7) -> torch.Tensor:
@@ -339,6 +384,7 @@ class B200Whisper:
         return out[:, :, :F]
 
     # ---- a6 ----
+    @_on_device
     def dtw(self, matrix: torch.Tensor, negate: bool = True, want_path: bool = False):
         """matrix fp32 [B, R, F] (row-strided view ok) -> jumps int32 [B, R] (+ path int32 [B, 2, R+F], len [B])."""
         B, R, F = matrix.shape

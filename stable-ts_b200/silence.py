@@ -8,9 +8,9 @@ The per-sample work (k-th largest magnitude, down-sampling, moving average, quan
 all windows of the batch at once; what is left on the host is the run-length bookkeeping on <= 1501 booleans per window,
 which the reference also keeps in numpy.  There is no CPU fallback: the audio must live on a CUDA device.
 
-STATUS: the CUDA kernel behind this module was written after round 1's GPU budget was spent; it is compiled and exported but
-has not run on hardware yet (tests/test_gpu_silence.py is the first thing to run in round 2).  Nothing on the default
-transcribe / align path calls it.
+``transcribe_windows(..., suppress_ts_tokens=True)`` feeds ``predict_nonvad_batch``'s per-window masks to the sampler
+(``ts_token_mask`` [B, 1501], original_whisper.py:504-511 / decode.py:14-16); bit-exact against the oracle and the
+reference-written fixtures on hardware (tests/test_gpu_silence.py).
 """
 from typing import List, Optional, Sequence
 

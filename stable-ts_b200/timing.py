@@ -69,7 +69,7 @@ def window_batch_forward(model: B200Whisper, tokenizer, jobs: List[WindowJob], *
             for i, j in enumerate(jobs):
                 a = j.audio.detach().float().flatten()[:N_SAMPLES]
                 audio[i, : a.numel()] = a
-        if not audio.is_pinned():
+        if audio.device.type == "cpu" and model.device.type == "cuda" and not audio.is_pinned():
             audio = audio.pin_memory()
         audio = audio.to(model.device, non_blocking=True)
         mel = model.log_mel(audio)                         # == log_mel_spectrogram(audio, padding=N_SAMPLES-n)
@@ -130,7 +130,8 @@ def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfi
         qk_g = qk if len(idx) == len(jobs) else qk.index_select(0, sel).contiguous()
         if new:
             kw = dict(aligner) if isinstance(aligner, dict) else {}
-            kw.pop("char_split", None)
+            if kw.pop("char_split", False):
+                raise NotImplementedError("B200 path: aligner={'char_split': True} is not implemented")
             # the reference slices [S:-1] of the decoder rows it ran (M_i = S + N + 2); padded rows are excluded by
             # running the scoring on a view of exactly those rows
             Mi = S + N + 2
@@ -372,33 +373,27 @@ def add_word_timestamps_stable(*, segments: List[dict], model: B200Whisper, toke
                                num_samples: int, prepend_punctuations: Optional[str] = PREPEND_PUNCT,
                                append_punctuations: Optional[str] = APPEND_PUNCT, enc=None, min_word_dur: float = 0.1,
                                split_callback: Optional[Callable] = None, gap_padding: Optional[str] = " ...",
-                               pad_first_seg: bool = True, aligner="legacy", **kwargs):
-    """Mutates ``segments[i]['words'|'start'|'end']`` in place (stable_whisper/timing.py:411-500)."""
+                               pad_first_seg: bool = True, aligner="legacy", mel: Optional[torch.Tensor] = None,
+                               audio_features: Optional[torch.Tensor] = None, ts_num: int = 0, ts_noise=None, **kwargs):
+    """Mutates ``segments[i]['words'|'start'|'end']`` in place (stable_whisper/timing.py:411-500).
+
+    The window is given as ``audio`` (fp32 samples; the log-mel then runs on the device), as ``mel`` [n_mels, 3000] (the
+    reference's argument, timing.py:416) or as ``enc`` / ``audio_features`` (encoder output, timing.py:421)."""
     if len(segments) == 0:
         return
+    if ts_num or ts_noise:
+        import warnings
+        warnings.warn("ts_num and ts_noise are deprecated and will be removed in future versions.", stacklevel=2)
     min_word_dur = min_word_dur or 0
     prepend_punctuations = PREPEND_PUNCT if prepend_punctuations is None else prepend_punctuations
     append_punctuations = APPEND_PUNCT if append_punctuations is None else append_punctuations
-    for seg in segments:
-        seg["words"] = []
-    text_tokens, token_split, seg_indices = split_word_tokens(segments, tokenizer, padding=gap_padding,
-                                                              split_callback=split_callback, pad_first_seg=pad_first_seg)
-    alignment = find_alignment_stable(model, tokenizer, text_tokens, audio, num_samples, token_split=token_split, enc=enc,
-                                      aligner=aligner, **kwargs)
-    alt_begin = pop_empty_alignment(alignment, seg_indices)
-    merge_punctuations(alignment, prepend_punctuations, append_punctuations)
-    offset = segments[0]["seek"]
-    assert len(alignment) == len(seg_indices)
-    assert gap_padding is None or len(segments) == len(alt_begin) + (1, 0)[pad_first_seg]
-    for i, timing in zip(seg_indices, alignment):
-        if len(timing.tokens) == 0:
-            continue
-        start, end = timing.start, timing.end
-        if len(segments[i]["words"]) == 0 and (end - start) < min_word_dur and i in alt_begin:
-            start = alt_begin[i].start
-        segments[i]["words"].append(dict(word=timing.word, start=round(offset + start, 3), end=round(offset + end, 3),
-                                         probability=timing.probability, tokens=timing.tokens))
-    for seg in segments:
-        if seg["words"]:
-            seg["start"] = seg["words"][0]["start"]
-            seg["end"] = seg["words"][-1]["end"]
+    if enc is None and audio_features is not None:
+        enc = model._encoding_of(audio_features)
+    if enc is None and audio is None and mel is not None:
+        enc = model.encode(mel.to(model.device, torch.float32))
+    text_tokens, words, word_tokens, seg_indices = _prepare_word_timestamps(segments, tokenizer, split_callback, gap_padding,
+                                                                            pad_first_seg)
+    alignment = find_alignment_stable(model, tokenizer, text_tokens, audio, num_samples, token_split=(words[:-1], word_tokens[:-1]),
+                                      enc=enc, aligner=aligner, **kwargs)
+    _finish_word_timestamps(segments, alignment, seg_indices, prepend_punctuations, append_punctuations, min_word_dur,
+                            gap_padding, pad_first_seg)

@@ -7,8 +7,12 @@ setting of SURVEY.md section 8e) are processed B at a time:
 
     log-mel -> encoder -> KV-cached greedy decode -> segment slicing at timestamp tokens -> batched word timestamps
 
-Out of scope here (reference control plane): silence suppression / VAD, temperature fallback,
-prompt conditioning, language detection, regrouping.
+Mirrored per-window behaviour: non-VAD silence masks -> ``ts_token_mask`` per window (``suppress_ts_tokens``,
+original_whisper.py:504-511), silent-window skip (:508-510), the no-speech / log-prob window skip (:537-547), segment
+pruning (:604-627), ``max_instant_words`` (:655-663) and the data-dependent seek (:703-710; ``transcribe`` walks every
+shard until its end, so speech after the last closed segment of a window is re-decoded exactly as the reference does).
+Out of scope here (reference control plane): VAD models, word-level ``suppress_silence`` re-timing
+(result.py), temperature fallback, prompt conditioning, language detection, regrouping.
 """
 from typing import List, Optional, Sequence
 
@@ -58,7 +62,7 @@ def slice_segments(tokens: Sequence[int], tokenizer, time_offset: float, segment
             end_pos = stamps[-1] - tb
             duration = min(end_pos * TIME_PRECISION, segment_duration)
         segments.append(seg(round(time_offset, 3), round(time_offset + duration, 3), toks))
-    return segments, end_pos
+    return segments, end_pos, single_ending
 
 
 @torch.no_grad()
@@ -66,9 +70,19 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                        word_timestamps: bool = True, options: Optional[DecodingOptions] = None,
                        ts_token_mask: Optional[torch.Tensor] = None, forced_tokens: Optional[torch.Tensor] = None,
                        gap_padding: Optional[str] = " ...", min_word_dur: float = 0.1, punctuations: str = "\"'“¿([{-\"'.。,，!！?？:：”)]}、",
-                       enc: Optional[dict] = None, n_samples: Optional[Sequence[int]] = None, use_graph: bool = True):
-    """B independent <=30 s windows -> list (per window) of segment dicts with ``words``.
-    ``enc`` (+ ``n_samples``) may be passed instead of ``audios`` when the encoder output is already on the device."""
+                       enc: Optional[dict] = None, n_samples: Optional[Sequence[int]] = None, use_graph: bool = True,
+                       suppress_ts_tokens: bool = False, skip_silent: bool = False, q_levels: int = 20, k_size: int = 5,
+                       no_speech_threshold: Optional[float] = None, logprob_threshold: Optional[float] = None,
+                       max_instant_words: Optional[float] = None):
+    """B independent <=30 s windows -> (list (per window) of segment dicts with ``words``, info).
+    ``enc`` (+ ``n_samples``) may be passed instead of ``audios`` when the encoder output is already on the device.
+
+    suppress_ts_tokens / skip_silent: run the batched non-VAD silence detector on the windows (silence.py); the former
+    feeds one ``ts_token_mask`` row per window to the sampler, the latter drops windows that are entirely silent.
+    no_speech_threshold / logprob_threshold / max_instant_words: the reference's per-window filters (transcribe_stable
+    defaults 0.6 / -1.0 / 0.5); None here = off, so that fixed-script benchmark windows are never dropped.
+    info["advance"][b]: samples the reference's seek would move by after this window (original_whisper.py:703-710)."""
+    dev_audio = None
     if enc is None:
         if torch.is_tensor(audios) and audios.ndim == 2 and audios.shape[1] == N_SAMPLES and audios.dtype == torch.float32:
             batch = audios                                   # already a [B, 480000] batch (ideally pinned): no host copy
@@ -82,24 +96,50 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                 a = a.detach().float().flatten()[:N_SAMPLES]
                 batch[i, : a.numel()] = a
                 n_samples.append(int(a.numel()))
-        if not batch.is_pinned():
+        if batch.device.type == "cpu" and not batch.is_pinned():
             batch = batch.pin_memory()
-        mel = model.log_mel(batch.to(model.device, non_blocking=True))
-        enc = model.encode(mel)
+        with torch.cuda.device(model.device):
+            dev_audio = batch.to(model.device, non_blocking=True)
+            mel = model.log_mel(dev_audio)
+            enc = model.encode(mel)
     B = enc["B"]
     n_samples = list(n_samples) if n_samples is not None else [N_SAMPLES] * B
     offs = list(time_offsets) if time_offsets is not None else [0.0] * B
     if options is None:                      # transcribe_stable defaults max_initial_timestamp to None (original_whisper.py:262-263)
         options = DecodingOptions(max_initial_timestamp=None)
+    silent = [False] * B
+    if suppress_ts_tokens or skip_silent:
+        if dev_audio is None:
+            raise ValueError("silence detection needs the window audio (pass `audios`, not only `enc`)")
+        from .silence import predict_nonvad_batch
+        masks = [None] * B
+        by_len = {}
+        for b, n in enumerate(n_samples):
+            by_len.setdefault(n, []).append(b)
+        for n, idx in by_len.items():        # the kernel takes equal-length rows: one launch per distinct window length
+            rows = dev_audio[idx][:, :n] if len(idx) != B else dev_audio[:, :n]
+            for b, pred in zip(idx, predict_nonvad_batch(rows, offsets=[offs[b] for b in idx], q_levels=q_levels, k_size=k_size,
+                                                         min_word_dur=min_word_dur)):
+                masks[b] = pred["mask"]
+                silent[b] = bool(pred["is_silent"]) and skip_silent
+        if suppress_ts_tokens and ts_token_mask is None and any(m is not None for m in masks):
+            ts_token_mask = masks
     # the cross K/V block and the KV cache live in model-owned buffers: they are consumed inside this call (decode loop, then
     # the alignment pass below) and are by far the largest allocations of a step
     results, extras = decode_windows(model, tokenizer, enc, options, ts_token_mask=ts_token_mask,
                                      forced_tokens=forced_tokens, use_graph=use_graph, reuse_buffers=True)
-    windows = []
+    windows, advance, skipped = [], [], []
     for b in range(B):
         dur = n_samples[b] / SAMPLE_RATE
         toks = results[b].tokens if forced_tokens is None else extras["step_tokens"][:, b].tolist()
-        segs, end_pos = slice_segments(toks, tokenizer, offs[b], dur, results[b]) if len(toks) else ([], 0)
+        skip = silent[b]
+        if not skip and no_speech_threshold is not None:          # original_whisper.py:537-547
+            skip = results[b].no_speech_prob > no_speech_threshold
+            if logprob_threshold is not None and results[b].avg_logprob > logprob_threshold:
+                skip = False
+        segs, end_pos, single_ending = ([], 0, False)
+        if not skip and len(toks):
+            segs, end_pos, single_ending = slice_segments(toks, tokenizer, offs[b], dur, results[b])
         # prune punctuation-only and zero-length segments (original_whisper.py:604-627, word_timestamps branch)
         # (`in` on a str is a substring test, so empty-text segments are dropped too, exactly as the reference does)
         segs = [s for s in segs if s["text"].strip() not in punctuations]
@@ -108,24 +148,51 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
             s["seek"] = offs[b]
         num = min(round(end_pos * N_SAMPLES_PER_TOKEN), n_samples[b]) if end_pos > 0 else n_samples[b]
         windows.append(dict(segments=segs, num_samples=num))
+        advance.append(n_samples[b] if (skip or single_ending or not len(toks)) else num)
+        skipped.append(bool(skip))
     if word_timestamps:
         add_word_timestamps_batch(windows, model, tokenizer, enc=enc, ckv=extras["ckv"], gap_padding=gap_padding,
                                   min_word_dur=min_word_dur)
+        if max_instant_words is not None:                          # original_whisper.py:655-663
+            for w in windows:
+                w["segments"] = [s for s in w["segments"] if not s["words"] or float(np.mean(np.array(
+                    [x["start"] == x["end"] for x in s["words"]]).astype(np.float16))) <= max_instant_words]
+    for b, w in enumerate(windows):
+        if not w["segments"]:
+            advance[b] = n_samples[b]                              # nothing kept: the reference fast-forwards the whole window
     return [w["segments"] for w in windows], dict(decode=results, steps=extras["steps"], step_argmax=extras["step_argmax"],
-                                                  step_tokens=extras["step_tokens"])
+                                                  step_tokens=extras["step_tokens"], advance=advance, skipped=skipped)
 
 
-def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_windows: int = 16, **kw) -> dict:
-    """Static 30 s sharding of one long audio (clip boundaries fixed at multiples of 30 s, no prompt carry-over).
+def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_windows: int = 16, shard_seconds: Optional[float] = 30.0,
+               no_speech_threshold: Optional[float] = 0.6, logprob_threshold: Optional[float] = -1.0,
+               max_instant_words: Optional[float] = 0.5, skip_silent: bool = True, **kw) -> dict:
+    """One long audio as static shards (clip boundaries at multiples of ``shard_seconds``, no prompt carry-over: the sharded
+    setting of SURVEY.md section 8e).  Inside a shard the walk is the reference's: a window starts at the shard's seek,
+    and the seek then moves by the data-dependent amount of original_whisper.py:703-710, so the tail after the last closed
+    segment of a window is decoded again by the next window.  Every round batches the current window of up to
+    ``batch_windows`` unfinished shards.  ``shard_seconds=None``: the whole audio is one shard (sequential, as the reference).
     -> dict(text, segments, language) in the shape of WhisperResult.to_dict (result.py:1398-1406)."""
     audio = audio.detach().float().flatten()
-    chunks = [audio[i:i + N_SAMPLES] for i in range(0, audio.numel(), N_SAMPLES)]
-    segments = []
-    for i in range(0, len(chunks), batch_windows):
-        part = chunks[i:i + batch_windows]
-        segs, _ = transcribe_windows(model, tokenizer, part, time_offsets=[(i + k) * 30.0 for k in range(len(part))], **kw)
-        for ws in segs:
-            segments.extend(ws)
+    total = int(audio.numel())
+    step = total if not shard_seconds else max(int(round(shard_seconds * SAMPLE_RATE)), 1)
+    shards = [[lo, min(lo + step, total)] for lo in range(0, max(total, 1), step)]          # [seek, end]
+    per_shard = [[] for _ in shards]
+    live = [i for i, (lo, hi) in enumerate(shards) if hi > lo]
+    while live:
+        now, live = live[:batch_windows], live[batch_windows:]
+        part = [audio[shards[i][0]: min(shards[i][0] + N_SAMPLES, shards[i][1])] for i in now]
+        segs, info = transcribe_windows(model, tokenizer, part, time_offsets=[shards[i][0] / SAMPLE_RATE for i in now],
+                                        no_speech_threshold=no_speech_threshold, logprob_threshold=logprob_threshold,
+                                        max_instant_words=max_instant_words, skip_silent=skip_silent, **kw)
+        again = []
+        for k, i in enumerate(now):
+            per_shard[i].extend(segs[k])
+            shards[i][0] += max(int(info["advance"][k]), 1)
+            if shards[i][0] < shards[i][1]:
+                again.append(i)
+        live = again + live
+    segments = [s for ps in per_shard for s in ps]
     for k, s in enumerate(segments):
         s["id"] = k
     return dict(text="".join(s["text"] for s in segments), segments=segments,

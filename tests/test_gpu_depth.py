@@ -3,9 +3,8 @@ weights at the full `small` (12+12 layers, BASELINE config 3) and `large-v3` (32
 
 Gates (BASELINE.json north_star): logits / QK / encoder output within 1e-3 relative (max |diff| / max |ref|), teacher-
 forced argmax rows equal, greedy token ids bit-exact, word start/end within +-20 ms, token probabilities 2e-3.
-The same tests print -- and bound -- what the cheaper arithmetic choices would cost at this depth (one fp16 tensor-core
-pass instead of three; fp16-only cross K/V in the decode step instead of the 3-byte format), so the precision choices of
-DESIGN.md section 3 rest on measurements at 32 layers, not on an extrapolation from 6.
+The same tests print what one fp16 tensor-core pass instead of three would cost at this depth, so the precision choices
+of DESIGN.md section 3 rest on measurements at 32 layers, not on an extrapolation from 6.
 CPU cost: one large-v3 window through the oracle is ~15-30 s on the GPU box's host cores."""
 import numpy as np
 import pytest
@@ -74,12 +73,12 @@ def test_full_depth_forward_matches_oracle(name):
     assert errs["fp16"]["logits"] < 5e-2          # sanity bound only: the single-pass mode is NOT the parity mode
 
 
-def test_large_v3_decode_step_variants_vs_oracle():
-    """a9 at 32 layers: forced 24-step script, per-step filtered logits and argmax vs the oracle for the default decode
-    step (3-byte cross K/V), the fp16-only cross K/V (`xkv_fp16`), the V2 cross-attention kernel, and one-pass fp16."""
+def test_large_v3_decode_step_vs_oracle():
+    """a9 at 32 layers: forced 24-step script, per-step filtered logits and argmax vs the oracle for the decode step (fp16
+    cross K/V planes) in the parity mode and, for the record, in one-pass fp16.  Round-2 measurement that decided the
+    format (gpurun_out/r2_depth/depth.log): 3-byte hi+int8-residual K/V 2.07e-5, fp16-only K/V 2.15e-5, gate 1e-3."""
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
-    from stable_ts_b200 import _lib as L
     from stable_ts_b200.decode import DecodingOptions, decode_windows
     from stable_ts_b200.model import from_oracle
     W, SP, model, otk, gm, tk = _build("large-v3", seed=6)
@@ -89,34 +88,25 @@ def test_large_v3_decode_step_variants_vs_oracle():
     mel_ref = W.pad_or_trim(W.log_mel_spectrogram(audio, model.dims.n_mels), 3000)
     ref, _, ex = SP.decode_window(model, mel_ref, forced_tokens=script, return_step_logits=True, sample_len=steps, language="en")
 
-    def run(g, **opts):
-        for k, v in opts.items():
-            L.set_option(k, v)
-        try:
-            enc = g.encode(g.log_mel(audio.cuda()[None]))
-            _, gx = decode_windows(g, tk, enc, DecodingOptions(language="en", sample_len=steps),
-                                   forced_tokens=torch.tensor(script)[:, None], return_step_logits=True)
-        finally:
-            for k in opts:
-                L.set_option(k, 0)
+    def run(g):
+        enc = g.encode(g.log_mel(audio.cuda()[None]))
+        res, gx = decode_windows(g, tk, enc, DecodingOptions(language="en", sample_len=steps),
+                                 forced_tokens=torch.tensor(script)[:, None], return_step_logits=True)
         worst = 0.0
         for i in range(steps):
             r, o = ex["step_logits"][i], gx["step_logits"][i][0].cpu()
             fin = r > -1e30
             assert torch.equal(fin, o > -1e30), f"mask mismatch at step {i}"
             worst = max(worst, ((o[fin] - r[fin]).abs().max() / r[fin].abs().max()).item())
-        return worst, gx["step_argmax"][:, 0].tolist() == ex["step_argmax"]
+        return worst, gx["step_argmax"][:, 0].tolist() == ex["step_argmax"], res[0].avg_logprob
 
-    out = {"fp16x3 + 3-byte cross K/V (default)": run(gm), "fp16x3 + fp16 cross K/V": run(gm, xkv_fp16=1),
-           "fp16x3 + 3-byte, xattn V2": run(gm, xattn_v2=1)}
-    g16 = from_oracle(model, precision="fp16")
-    out["fp16 single pass"] = run(g16)
-    for k, (w, eq) in out.items():
-        print(f"[large-v3 decode step, {steps} steps] {k}: worst step-logit rel {w:.2e}, argmax bit-exact {eq}")
-    w, eq = out["fp16x3 + 3-byte cross K/V (default)"]
-    assert w < 1e-3 and eq
-    w, eq = out["fp16x3 + 3-byte, xattn V2"]
-    assert w < 1e-3 and eq
+    out = {"fp16x3 (parity mode)": run(gm)}
+    out["fp16 single pass"] = run(from_oracle(model, precision="fp16"))
+    for k, (w, eq, lp) in out.items():
+        print(f"[large-v3 decode step, {steps} steps] {k}: worst step-logit rel {w:.2e}, argmax bit-exact {eq}, "
+              f"avg_logprob {lp:.5f} (oracle {ref.avg_logprob:.5f})")
+    w, eq, lp = out["fp16x3 (parity mode)"]
+    assert w < 1e-3 and eq and abs(lp - ref.avg_logprob) < 1e-3
 
 
 @pytest.mark.parametrize("name,steps", [("small", 64), ("large-v3", 224)])

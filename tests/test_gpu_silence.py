@@ -1,17 +1,14 @@
 """GPU parity of the silence-detection kernel against the CPU oracle and the fixtures written by
 the unmodified reference: loudness and masks must be BIT-identical (fp32 arithmetic restated operation by operation).
 
-The kernel was written after round 1's GPU budget was spent and has not run on hardware yet, so this file only runs when
-STB_UNVERIFIED_KERNELS=1 is set; it is the first thing to run (and un-gate) in round 2."""
+First hardware run: round 2 (gpurun_out/r2_first/silence_tests.log, 3 passed)."""
 import os
 
 import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("STB_UNVERIFIED_KERNELS") != "1",
-                                 reason="silence kernel not yet run on hardware (set STB_UNVERIFIED_KERNELS=1)")]
+pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "silence_cases.npz")
 
 

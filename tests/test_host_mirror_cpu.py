@@ -111,13 +111,13 @@ def test_slice_segments_matches_whisper_rules():
         compression_ratio = 1.0
         no_speech_prob = 0.0
     toks = [tb + 0, 300, 301, tb + 100, tb + 100, 302, tb + 250, tb + 250, 303]      # two closed pairs + open tail
-    segs, end_pos = slice_segments(toks, tk, time_offset=30.0, segment_duration=30.0, result=R)
+    segs, end_pos, _ = slice_segments(toks, tk, time_offset=30.0, segment_duration=30.0, result=R)
     assert [(s["start"], s["end"]) for s in segs] == [(30.0, 32.0), (32.0, 35.0)] and end_pos == 250
     assert segs[0]["tokens"] == toks[:4] and segs[1]["tokens"] == toks[4:7]
     toks = [300, 301, tb + 75]                                                        # single timestamp ending
-    segs, end_pos = slice_segments(toks, tk, 0.0, 30.0, R)
+    segs, end_pos, _ = slice_segments(toks, tk, 0.0, 30.0, R)
     assert len(segs) == 1 and segs[0]["end"] == 1.5 and end_pos == 75
-    segs, end_pos = slice_segments([300, 301], tk, 0.0, 12.5, R)                      # no timestamps at all
+    segs, end_pos, _ = slice_segments([300, 301], tk, 0.0, 12.5, R)                      # no timestamps at all
     assert len(segs) == 1 and (segs[0]["start"], segs[0]["end"]) == (0.0, 12.5) and end_pos == 0
 
 
