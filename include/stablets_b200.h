@@ -244,6 +244,14 @@ STB_API int stb_silence_mask(const float* audio, int B, int n_samples, long long
                              int k_size, const float* thr_in, float* loudness_out, uint8_t* mask_out, float* thr_out,
                              void* stream);
 
+/* Section 8(f) row 3 -- audio ingest (replaces the ffmpeg pipe of stable_whisper/audio/utils.py:96-125 for PCM/WAV input):
+ *    interleaved PCM [n_frames_in][channels] (sample_format 0 = s16, 1 = s32, 2 = f32) -> mono fp32 at rate * L / M:
+ *    equal-weight down-mix, polyphase FIR y[m] = sum_j table[(m M) mod L][j] * x[(m M) div L - taps/2 + j] (zero outside the
+ *    input), table [L][taps] fp32 built by the caller (stable-ts_b200/audio_io.py: Kaiser-windowed sinc, DC gain 1), taps odd.
+ *    quantize_s16 != 0 rounds the result to the int16 grid, as the reference's `-f s16le` pipe does. */
+STB_API int stb_resample_mono(const void* pcm, int sample_format, int channels, long long n_frames_in, int L, int M,
+                      const float* table, int taps, float* out, long long n_out, int quantize_s16, void* stream);
+
 /* a9 KV-cached decode (stable_whisper/decode.py:33-65; whisper PyTorchInference.logits + logit filters +
  *    GreedyDecoder.update).  One step = one decoder forward for the newest token of B sequences.
  *    Everything position-dependent is read from the DEVICE counter `pos` (index of the token being fed), which the step

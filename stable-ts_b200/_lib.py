@@ -54,6 +54,8 @@ _SIGS = {
                               c_void_p, c_longlong, c_longlong, c_longlong, c_void_p]),
     "stb_silence_mask": (c_int, [c_void_p, c_int, c_int, c_longlong, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
+    "stb_resample_mono": (c_int, [c_void_p, c_int, c_int, c_longlong, c_int, c_int, c_void_p, c_int, c_void_p, c_longlong, c_int,
+                                  c_void_p]),
     "stb_gemv": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_longlong,
                          c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "stb_split_f16": (c_int, [c_void_p, c_longlong, c_int, c_longlong, c_void_p, c_void_p, c_longlong, c_void_p]),

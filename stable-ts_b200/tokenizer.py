@@ -110,6 +110,10 @@ class Tokenizer:
 
     @cached_property
     def non_speech_tokens(self):
+        if isinstance(self.codec, _SyntheticCodec):
+            # the stand-in vocabulary has no multi-character pieces: the set is the single-byte ids of whisper's ASCII symbol
+            # list plus "-" and "'" (the same definition as the oracle's stand-in tokenizer, oracle/whisper_ref/tokenizer.py)
+            return tuple(sorted({ord(c) for c in '"#()*+/:;<=>@[\\]^_`{|}~'} | {ord("-"), ord("'")}))
         symbols = list('"#()*+/:;<=>@[\\]^_`{|}~「」『』') + "<< >> <<< >>> -- --- -( -[ (' (\" (( )) ((( ))) [[ ]] {{ }} ♪♪ ♪♪♪".split()
         misc = set("♩♪♫♬♭♮♯")
         result = {self.encode(" -")[0], self.encode(" '")[0]}

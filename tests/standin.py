@@ -30,6 +30,9 @@ class OracleBackedModel(WhisperProtocol):
         self.alignment_head_pairs = SP.head_pairs_of(oracle_model)
         self._want_lo = False
         self.calls: Dict[str, int] = {}
+        # whisper model-object protocol (shim.py on the real model): here the oracle's own modules
+        self.encoder, self.decoder = oracle_model.encoder, oracle_model.decoder
+        self.install_kv_cache_hooks = oracle_model.install_kv_cache_hooks
 
     is_multilingual = property(lambda self: self.om.is_multilingual)
     num_languages = property(lambda self: self.om.num_languages)

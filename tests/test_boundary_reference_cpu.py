@@ -110,3 +110,32 @@ def test_own_result_schema_loads_in_the_reference(env):
         assert set(sb) <= set(sa)
         for wa, wb in zip(sa.get("words") or [], sb.get("words") or []):
             assert wa == wb
+
+
+@pytest.mark.parametrize("mode,thr", [(2, 0.5), (0, 0.0), (1, 0.0), (0, 0.5)])
+def test_locate_matches_unmodified_reference(env, mode, thr):
+    """stable_ts_b200.locate (host loop + kernel calls) over the stand-in == stable_whisper.alignment.locate over the oracle
+    model (alignment.py:756-1116): target times (mode 2), confirmed segments with word timings (mode 0), window words (mode 1)."""
+    import stable_whisper.alignment as ref_align
+    from stable_ts_b200 import api
+    stand = api.modify_model(env["stand"])
+    text = [700, 901, 333]
+    kw = dict(count=3, mode=mode, probability_threshold=thr, exact_token=True, max_token_per_seg=8, verbose=None)
+    theirs = ref_align.locate(env["model"], env["audio"], text, "en", **kw)
+    mine = stand.locate(env["audio"], text, "en", **{k: v for k, v in kw.items() if k != "verbose"})
+    assert len(mine) == len(theirs)
+    if mode != 0 or thr == 0.0:
+        assert len(mine) > 0
+    for a, b in zip(mine, theirs):
+        if mode == 2:
+            assert a == b
+        elif mode == 1:
+            assert a["end"] == b["end"] and a["duration_window_text"] == b["duration_window_text"]
+            assert [w["tokens"] for w in a["duration_window_word"]] == [w["tokens"] for w in b["duration_window_word"]]
+            np.testing.assert_allclose([w["probability"] for w in a["duration_window_word"]],
+                                       [w["probability"] for w in b["duration_window_word"]], rtol=1e-5)
+        else:
+            da, db = a.to_dict(), b.to_dict()
+            assert da["seek"] == db["seek"] and da["start"] == db["start"] and da["end"] == db["end"]
+            assert [(w["word"], w["tokens"], w["start"], w["end"]) for w in da["words"]] == \
+                   [(w["word"], w["tokens"], w["start"], w["end"]) for w in db["words"]]
