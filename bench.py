@@ -44,9 +44,11 @@ def parse():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--model", default="large-v3")
-    p.add_argument("--workload", default="transcribe", choices=["transcribe", "align"],
+    p.add_argument("--workload", default="transcribe", choices=["transcribe", "align", "refine"],
                    help="transcribe: 224 forced KV-cached decode steps + word timestamps (BASELINE configs 2/4 shape); "
-                        "align: forced alignment of a 100-token script (configs 1/3 shape)")
+                        "align: forced alignment of a 100-token script (configs 1/3 shape); refine: the Refiner's inference "
+                        "call (config 5): per group a [2, 480000] audio pair + token script -> probabilities and ranks, group "
+                        "lengths cycling 442 / 442 / 116 tokens (a 1000-token script = 3 groups); --windows = groups per step")
     p.add_argument("--windows", type=int, default=120,
                    help="30 s windows per GPU per step (120 = one rank's share of BASELINE config 4: 8 h of audio over 8 GPUs)")
     p.add_argument("--tokens", type=int, default=None, help="text tokens per window (default: 224 transcribe / 100 align)")
@@ -60,7 +62,26 @@ def parse():
     a = p.parse_args()
     if a.tokens is None:
         a.tokens = 224 if a.workload == "transcribe" else 100
+    if a.workload == "refine" and a.windows == 120:
+        a.windows = 3                                       # config 5: one 1000-token script = 3 refine groups
     return a
+
+
+REFINE_LENS = (442, 442, 116)
+
+
+def make_refine_groups(n, eot, seed0):
+    """n refine groups: (audio pair fp32 [2, 480000] -- the second row with a muted span, as the Refiner produces --, tokens)"""
+    groups = []
+    for i in range(n):
+        a = synth_audio(N_SAMPLES, seed0 + i)
+        pair = torch.stack([a, a.clone()])
+        g = torch.Generator().manual_seed(977 + seed0 + i)
+        lo = int(torch.randint(0, N_SAMPLES - 40000, (1,), generator=g))
+        pair[1, lo:lo + 40000] = 0
+        toks = torch.randint(256, eot, (REFINE_LENS[i % 3],), generator=g).tolist()
+        groups.append((pair, toks))
+    return groups
 
 
 # ------------------------------------------------------------------------------------------------- synthetic workload
@@ -191,8 +212,19 @@ def cpu_arm(args, dims_tuple, n_windows, threads=None):
         model.set_alignment_heads(mask)
         tk = W.tokenizer.get_tokenizer(model.is_multilingual, num_languages=model.num_languages, language="en",
                                        task="transcribe")
-        _CPU.update(model=model, tk=tk, data=make_windows(n_windows, args.tokens, tk.eot, seed0=1000))
+        _CPU.update(model=model, tk=tk, data=make_windows(n_windows, args.tokens, tk.eot, seed0=1000) if args.workload != "refine"
+                    else make_refine_groups(n_windows, tk.eot, seed0=1000))
     model, tk = _CPU["model"], _CPU["tk"]
+    if args.workload == "refine":
+        t0 = time.perf_counter()
+        detail, n_tok = [], 0
+        for pair, toks in _CPU["data"]:
+            p, r = SP.prob_and_rank(SP.refine_token_probs(model, tk, pair, toks), toks)
+            detail.append(dict(p=p, rank=r))
+            n_tok += len(toks)
+        dt = time.perf_counter() - t0
+        _CPU["detail"] = detail
+        return n_windows * AUDIO_S / dt, n_tok / dt, dt, cores
     audios, wts = _CPU["data"]
     t0 = time.perf_counter()
     n_words = 0
@@ -261,6 +293,15 @@ def run_reference(args, dims_tuple):
     print(json.dumps(out), flush=True)
 
 
+def parity_refine(p, r, cpu):
+    """Group 0 of the refine workload: probabilities within 2e-3 of the CPU oracle's; ranks equal except where the oracle
+    itself has classes within that tolerance of the target (counted, not hidden)."""
+    rel = float(((p - cpu["p"]).abs() / cpu["p"].clamp_min(1e-30)).max())
+    eq = int((r.long() == cpu["rank"]).sum())
+    return {"group": 0, "tokens": int(p.numel()), "prob_rel": float(f"{rel:.3e}"), "ranks_equal": eq,
+            "rank_max_delta": int((r.long() - cpu["rank"]).abs().max()), "ok": bool(rel <= 2e-3)}
+
+
 def ncu_traffic(kernel: str, algorithmic_bytes_per_launch: float):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` export of this workload (profiles/r2_ncu_*.csv:
     dram__bytes_read.sum + dram__bytes_write.sum, raw page).  Only used when the capture's launch moved the same
@@ -315,20 +356,31 @@ def run_b200(args, dims_tuple):
     S = len(tk.sot_sequence)
     Wn = args.windows
     pools = 2                                           # rotate distinct inputs between steps
-    batches = [make_windows(Wn, args.tokens, tk.eot, seed0=1000 + 100000 * rank + 1000 * p) for p in range(pools)]
-    n_words_step = sum(len(w) for w in batches[0][1])
-    host_audio = [torch.stack(b[0]).pin_memory() for b in batches]
-    dev_audio = [h.to(dev) for h in host_audio]
-    jobs = [[WindowJob([t for w in wt for t in w], N_SAMPLES, None) for wt in b[1]] for b in batches]
+    refine = args.workload == "refine"
+    if refine:
+        from stable_ts_b200.alignment import refine_probs
+        groups = [make_refine_groups(Wn, tk.eot, seed0=1000 + 100000 * rank + 1000 * p) for p in range(pools)]
+        host_pairs = [[g[0].pin_memory() for g in gp] for gp in groups]
+        dev_pairs = [[h.to(dev) for h in hp] for hp in host_pairs]
+        batches = [([], [[g[1]] for g in gp]) for gp in groups]          # token scripts in the (audios, word_tokens) shape used below
+        host_audio = dev_audio = jobs = None
+    else:
+        batches = [make_windows(Wn, args.tokens, tk.eot, seed0=1000 + 100000 * rank + 1000 * p) for p in range(pools)]
+        host_audio = [torch.stack(b[0]).pin_memory() for b in batches]
+        dev_audio = [h.to(dev) for h in host_audio]
+        jobs = [[WindowJob([t for w in wt for t in w], N_SAMPLES, None) for wt in b[1]] for b in batches]
 
     from stable_ts_b200.decode import DecodingOptions
     from stable_ts_b200.sharding import run_sharded
     from stable_ts_b200.transcribe import transcribe_windows
-    scripts = [torch.tensor([[t for w in wt for t in w] for wt in b[1]], dtype=torch.int32).T.contiguous() for b in batches]
+    scripts = None if refine else [torch.tensor([[t for w in wt for t in w] for wt in b[1]], dtype=torch.int32).T.contiguous()
+                                   for b in batches]
     dopt = DecodingOptions(language="en", sample_len=args.tokens, max_initial_timestamp=None)
 
     def device_step(p, use_graph=True):
         """hot path with inputs resident in HBM; only the tiny jumps/probs/token tables are read back"""
+        if refine:                                   # refinement.py:291: one inference call per group, [2, n] audio + script
+            return [refine_probs(model, tk, pair, g[1]) for pair, g in zip(dev_pairs[p], groups[p])]
         enc = model.encode(model.log_mel(dev_audio[p]))
         if args.workload == "align":
             return align_windows(model, tk, jobs[p], enc=enc)
@@ -349,6 +401,8 @@ def run_b200(args, dims_tuple):
     # other buffer offsets), must give the same words -- catches index overflow / layout faults that only show at 100+ windows
     selfcheck = None
     gpu_w0 = None                                       # window 0 of pool 0 (rank 0): compared with the CPU oracle below
+    if refine and rank == 0 and not args.ncu:
+        gpu_w0 = refine_probs(model, tk, host_pairs[0][0], groups[0][0][1])
     if args.workload == "align" and rank == 0 and not args.ncu:
         gpu_w0 = (align_words_batch(model, tk, [host_audio[0][0]], [batches[0][1][0]])[0], None)
     if args.workload == "transcribe" and rank == 0 and not args.ncu:
@@ -406,6 +460,17 @@ def run_b200(args, dims_tuple):
 
     # ---- e2e: public API with host buffers (+ the one gather of word records when N > 1)
     def e2e_step(p):
+        if refine:                                # pinned host pairs in, host probabilities + ranks out (+ one gather when N > 1)
+            out = [refine_probs(model, tk, pair, g[1]) for pair, g in zip(host_pairs[p], groups[p])]
+            flat = torch.cat([torch.cat([pr.flatten(), rk.flatten().float()]) for pr, rk in out])
+            if world > 1:
+                parts = [torch.empty_like(flat) for _ in range(world)]
+                dist.all_gather(parts, flat)
+                flat = torch.cat(parts)
+            res = flat.cpu()
+            res.n_words = world * sum(len(g[1]) for g in groups[p])
+            return res
+
         def process(lo, hi):                      # this rank's windows (weak scaling: Wn per rank)
             if args.workload == "align":
                 return align_words_batch(model, tk, list(host_audio[p]), batches[p][1])
@@ -506,7 +571,8 @@ def run_b200(args, dims_tuple):
                          f"reference CPU path, fp32, torch threads = {cores}"}
         if gpu_w0 is not None:                          # same window (audio seed 1000, script, weights) through both paths
             try:
-                parity = parity_vs_cpu(gpu_w0[0], gpu_w0[1], _CPU["detail"][0])
+                parity = (parity_refine(gpu_w0[0].cpu(), gpu_w0[1].cpu(), _CPU["detail"][0]) if refine else
+                          parity_vs_cpu(gpu_w0[0], gpu_w0[1], _CPU["detail"][0]))
             except Exception as e:
                 parity = {"ok": None, "detail": f"parity check did not run: {type(e).__name__}: {e}"}
             print(f"[bench] parity_vs_cpu: {parity}", file=sys.stderr)
@@ -521,16 +587,20 @@ def run_b200(args, dims_tuple):
         "config": {"workload": (f"transcribe+word_timestamps {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} forced "
                                 "KV-cached decode steps then word alignment (BASELINE configs 2/4 shape)") if args.workload == "transcribe"
                    else (f"align {args.model}: {Wn} windows of 30 s per GPU per step, {args.tokens} text tokens/window "
-                         "(BASELINE configs 1/3 shape)"),
+                         "(BASELINE configs 1/3 shape)") if args.workload == "align"
+                   else (f"refine {args.model}: {Wn} refine groups per GPU per step, each one inference call of the Refiner: audio "
+                         "[2, 480000] + script of 442 / 442 / 116 tokens -> probabilities and ranks (BASELINE config 5 shape)"),
                    "weights": "seeded random init at true shapes", "precision": args.precision,
                    "alignment_heads": args.alignment_heads,
                    "l2": "per-step working set (weights 6.2 GB + activations) >> 126 MB L2; inputs rotate between 2 pools"},
         "rtf": 1.0 / value, "aligned_words_per_s": n_words_total / (ms_step / 1e3),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_other": roof_other, "kernels": kernels,
         "cpu_baseline": cpu, "parity_vs_cpu": parity,
-        "e2e": {"value": e2e_value, "unit": "audio_s/s", "h2d_bytes_per_step": Wn * N_SAMPLES * 4,
-                # jumps int32 [N+1] + token probs fp32 [N] per window (+ token/argmax tables and sampler state for decode)
-                "d2h_bytes_per_step": int(Wn * ((args.tokens + 3) * 4 + (args.tokens + 2) * 4)
+        "e2e": {"value": e2e_value, "unit": "audio_s/s", "h2d_bytes_per_step": Wn * N_SAMPLES * 4 * (2 if refine else 1),
+                # jumps int32 [N+1] + token probs fp32 [N] per window (+ token/argmax tables and sampler state for decode);
+                # refine: probabilities + ranks [2, N] per group
+                "d2h_bytes_per_step": int(sum(2 * 2 * 4 * len(g[1]) for g in groups[0])) if refine else
+                                      int(Wn * ((args.tokens + 3) * 4 + (args.tokens + 2) * 4)
                                           + (Wn * (2 * args.tokens * 4 + 24 + 4) if args.workload == "transcribe" else 0)),
                 "ms_per_step": e2e_s * 1e3, "aligned_words_per_s": n_words_total / e2e_s},
     }

@@ -125,7 +125,7 @@ def check(rc: int):
 
 
 def set_option(name: str, value: int):
-    """Run-time kernel-variant switch (stb_set_option): "xattn_v2", "decode_chain", "xkv_fp16"."""
+    """Run-time kernel-variant switch (stb_set_option): "decode_splitk_legacy" (A/B timing of the decode-step linears)."""
     check(lib().stb_set_option(name.encode(), int(value)))
 
 

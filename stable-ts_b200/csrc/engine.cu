@@ -404,7 +404,6 @@ struct StepWs {
     int* tickets;
     Split ln, attn, hid;
     float* part;       // split-K partials [split][B][N] of the swapped tcgen05 decode linears
-    unsigned int* chain_bar;   // grid-barrier words of the experimental chain kernel (zero-initialised workspace)
     size_t bytes;
 };
 constexpr int STEP_GEMV_MAX_B = 16;      // <= : mma.sync batched GEMV; above: swapped split-K tcgen05 GEMM
@@ -435,7 +434,6 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.attn = take_split(c, (size_t)B * d, lo);
     w.hid = take_split(c, (size_t)B * 4 * d, lo);
     w.part = (B > step_gemv_max_b() && B <= STEP_SPLITK_MAX_B) ? c.take<float>((size_t)B * STEP_SPLITK_TILES * 128) : nullptr;
-    w.chain_bar = c.take<unsigned int>(64);
     w.bytes = c.off;
     return w;
 }
@@ -462,6 +460,7 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     //   > 128        : the plain tcgen05 GEMM (sequences on the M side)
     const bool use_gemv = B <= step_gemv_max_b(), use_splitk = !use_gemv && B <= STEP_SPLITK_MAX_B;
     static const int tile_budget = env_int("STB_STEP_SPLIT_TILES", sm_count(), 1, STEP_SPLITK_TILES);
+    const bool legacy_splitk = option(OPT_DECODE_SPLITK_LEGACY) != 0;
     const Split none = {nullptr, nullptr};
     // ln_g != nullptr: also produce LayerNorm(out)*ln_g+ln_b into w.ln (only with a residual, out_f32 = w.x)
     auto lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
@@ -469,6 +468,9 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
                    const float* ln_b) -> int {
         if (use_gemv) {
             STB_TRY(gemv(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st));
+        } else if (use_splitk && !legacy_splitk && k % 64 == 0 && n >= 128) {
+            // one launch: cluster split-K + DSMEM reduction + fused epilogue (decode_linear.cu)
+            STB_TRY(decode_linear(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st));
         } else if (use_splitk) {
             const int mt = cdiv(n, 128), nkb = k / 64;
             int split = 1;
@@ -514,68 +516,6 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
         STB_TRY(layernorm(w.x, B, d, W_F32(m->dec[0], STB_L_ATTN_LN_G), W_F32(m->dec[0], STB_L_ATTN_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
     else
         STB_TRY(layernorm(w.x, B, d, final_g, final_b, w.ln.hi, w.ln.lo, nullptr, st));
-    if (use_splitk && decode_chain_enabled()) {
-        // EXPERIMENTAL (STB_DECODE_CHAIN=1): the linears between two attention kernels run as ONE persistent kernel each
-        // (gemm_chain.cu): [qkv] | self-attn | [out, +LN, cross-q] | cross-attn | [cross-out, +LN, fc1, fc2, +LN, next qkv] ...
-        const bool lo = m->prec == STB_PREC_FP16X3;
-        auto split_for = [&](int n, int k) {
-            const int mt = cdiv(n, 128), nkb = k / 64;
-            int split = 1;
-            for (int sdiv = 1; sdiv <= nkb; ++sdiv)
-                if (nkb % sdiv == 0 && (long long)mt * sdiv <= tile_budget && mt * sdiv <= STEP_SPLITK_TILES) split = sdiv;
-            return split;
-        };
-        struct ChainHolder {
-            ChainBuilder* cb;
-            ChainHolder() : cb(chain_new()) {}
-            ~ChainHolder() { chain_free(cb); }
-        } holder;
-        ChainBuilder& cb = *holder.cb;
-        auto add_lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
-                           const float* res, float* out_f32, Split out_split, long long ld, const float* ln_g,
-                           const float* ln_b) -> int {
-            const int split = split_for(n, k);
-            STB_TRY(chain_add_gemm(cb, w_hi, w_lo, n, k, x.hi, x.lo, split, w.part, nullptr, 0));
-            return chain_add_finish(cb, w.part, split, n, bias, act, res, out_f32, out_split.hi, out_split.lo, ld, ln_g, ln_b,
-                                    ln_g ? w.ln.hi : nullptr, ln_g ? w.ln.lo : nullptr);
-        };
-        chain_begin(cb, B, w.chain_bar, lo);
-        STB_TRY(add_lin(w.ln, d, W_HI(m->dec[0], STB_L_QKV_W), W_LO(m->dec[0], STB_L_QKV_W), 3 * d, W_F32(m->dec[0], STB_L_QKV_B),
-                        STB_ACT_NONE, nullptr, w.qkv, none, 3 * d, nullptr, nullptr));
-        STB_TRY(chain_launch(cb, st));
-        for (int l = 0; l < D.n_text_layer; ++l) {
-            const stb_model::Layer& L = m->dec[l];
-            const bool last = l + 1 == D.n_text_layer;
-            const float* next_g = last ? final_g : W_F32(m->dec[l + 1], STB_L_ATTN_LN_G);
-            const float* next_b = last ? final_b : W_F32(m->dec[l + 1], STB_L_ATTN_LN_B);
-            float* Kc = (float*)state + (size_t)l * 2 * cache;
-            float* Vc = Kc + cache;
-            STB_TRY(decode_attn_self(w.qkv, Kc, Vc, B, H, d, ctx, pos, w.attn.hi, w.attn.lo, nullptr, st));
-            chain_begin(cb, B, w.chain_bar, lo);
-            STB_TRY(add_lin(w.attn, d, W_HI(L, STB_L_OUT_W), W_LO(L, STB_L_OUT_W), d, W_F32(L, STB_L_OUT_B), STB_ACT_NONE, w.x, w.x,
-                            none, d, W_F32(L, STB_L_CROSS_LN_G), W_F32(L, STB_L_CROSS_LN_B)));
-            STB_TRY(add_lin(w.ln, d, W_HI(L, STB_L_CQ_W), W_LO(L, STB_L_CQ_W), d, W_F32(L, STB_L_CQ_B), STB_ACT_NONE, nullptr, w.q,
-                            none, d, nullptr, nullptr));
-            STB_TRY(chain_launch(cb, st));
-            Split Kx, vTx;
-            CrossDecodeKV Vd;
-            cross_ptrs(m, B, ckv, l, Kx, vTx, &Vd);
-            STB_TRY(decode_attn_cross(w.q, Vd, B, H, d, w.xpart, w.tickets, w.attn.hi, w.attn.lo, nullptr, st));
-            chain_begin(cb, B, w.chain_bar, lo);
-            STB_TRY(add_lin(w.attn, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d, W_F32(L, STB_L_COUT_B), STB_ACT_NONE, w.x,
-                            w.x, none, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B)));
-            STB_TRY(add_lin(w.ln, d, W_HI(L, STB_L_FC1_W), W_LO(L, STB_L_FC1_W), 4 * d, W_F32(L, STB_L_FC1_B), STB_ACT_GELU, nullptr,
-                            nullptr, w.hid, 4 * d, nullptr, nullptr));
-            STB_TRY(add_lin(w.hid, 4 * d, W_HI(L, STB_L_FC2_W), W_LO(L, STB_L_FC2_W), d, W_F32(L, STB_L_FC2_B), STB_ACT_NONE, w.x,
-                            w.x, none, d, next_g, next_b));
-            if (!last) {
-                const stb_model::Layer& Ln = m->dec[l + 1];
-                STB_TRY(add_lin(w.ln, d, W_HI(Ln, STB_L_QKV_W), W_LO(Ln, STB_L_QKV_W), 3 * d, W_F32(Ln, STB_L_QKV_B), STB_ACT_NONE,
-                                nullptr, w.qkv, none, 3 * d, nullptr, nullptr));
-            }
-            STB_TRY(chain_launch(cb, st));
-        }
-    } else
     for (int l = 0; l < D.n_text_layer; ++l) {
         const stb_model::Layer& L = m->dec[l];
         const bool last = l + 1 == D.n_text_layer;

@@ -53,18 +53,12 @@ int gemv(const void* x_hi, const void* x_lo, int B, int K, const void* w_hi, con
 int splitk_finish(const float* P, int split, int B, int N, const float* bias, int act, const float* res, long long ld_res,
                   float* out_f32, void* out_hi, void* out_lo, long long ld_out, const float* ln_g, const float* ln_b,
                   void* ln_hi, void* ln_lo, cudaStream_t st);
-// experimental persistent chain of decode-step linears (gemm_chain.cu; STB_DECODE_CHAIN=1)
-struct ChainBuilder;
-bool decode_chain_enabled();
-ChainBuilder* chain_new();
-void chain_free(ChainBuilder* cb);
-void chain_begin(ChainBuilder& cb, int B, unsigned int* bar, bool lo);
-int chain_add_gemm(ChainBuilder& cb, const void* w_hi, const void* w_lo, int n, int k, const void* x_hi, const void* x_lo,
-                   int split, float* partial, float* direct_out, long long ld_direct);
-int chain_add_finish(ChainBuilder& cb, const float* P, int split, int N, const float* bias, int act, const float* res,
-                     float* out_f32, void* out_hi, void* out_lo, long long ld, const float* ln_g, const float* ln_b, void* ln_hi,
-                     void* ln_lo);
-int chain_launch(const ChainBuilder& cb, cudaStream_t st);
+// one Linear of the decode step in one launch: swapped tcgen05 GEMM, split-K across a thread-block cluster, partial tiles
+// reduced over distributed shared memory, fused bias / GELU / residual epilogue (decode_linear.cu)
+int decode_linear(const void* x_hi, const void* x_lo, int B, int k, const void* w_hi, const void* w_lo, int n, const float* bias,
+                  int act, const float* res, long long ld_res, float* out_f32, void* out_hi, void* out_lo, long long ld_out,
+                  cudaStream_t st);
+int decode_linear_split(int n, int k);
 int embed_step(const int32_t* tokens, const int32_t* pos, int B, int d, const float* emb, const float* posemb, float* x,
                cudaStream_t st);
 int bump_pos(int32_t* pos, cudaStream_t st);

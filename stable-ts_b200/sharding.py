@@ -4,8 +4,13 @@ word records at the end (NCCL over NVLink on the GPU box; the same code runs ove
 
 Record buffer (int32, one per rank, identical capacity on every rank so a single all_gather suffices):
     [0]                      number of words n
-    [1 : 1+5*cap_words]      n x (window_id, start_ms, end_ms, n_tokens, probability as fp32 bits)
-    [1+5*cap_words : ]       token ids of the words, concatenated
+    [1 : 1+6*cap_words]      n x (window_id, start_ms, end_ms, n_tokens, probability as fp32 bits, segment index in the window)
+    [1+6*cap_words : ]       token ids of the words, concatenated
+
+The gathered records ARE the result wire format: ``gathered_to_result`` rebuilds, on any rank,
+the dict of ``WhisperResult.to_dict`` (stable_whisper/result.py:618-636 segment dict, :1398-1406 result dict) -- word text is
+re-decoded from the token ids, segment text / span / tokens from the words -- and ``result.make_result`` turns it into the
+reference's ``WhisperResult`` (or the schema-compatible stand-in).
 """
 from typing import Callable, List, Optional, Sequence, Tuple
 
@@ -14,6 +19,7 @@ import torch
 import torch.distributed as dist
 
 MAX_TOKENS_PER_WINDOW = 448
+REC = 6                      # int32 fields per word record
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -29,7 +35,7 @@ def capacity(n_windows_total: int, world: int) -> Tuple[int, int]:
 
 
 def pack_records(results: List[List[dict]], first_window: int, cap_words: int, cap_tokens: int) -> torch.Tensor:
-    buf = np.zeros(1 + 5 * cap_words + cap_tokens, dtype=np.int32)
+    buf = np.zeros(1 + REC * cap_words + cap_tokens, dtype=np.int32)
     flat = [(first_window + w, wd) for w, words in enumerate(results) for wd in words]
     n = len(flat)
     tok_lists = [wd["tokens"] for _, wd in flat]
@@ -37,13 +43,14 @@ def pack_records(results: List[List[dict]], first_window: int, cap_words: int, c
     t = int(counts.sum())
     assert n <= cap_words and t <= cap_tokens, "word record capacity exceeded"
     if n:
-        recs = buf[1:1 + 5 * n].reshape(n, 5)
+        recs = buf[1:1 + REC * n].reshape(n, REC)
         recs[:, 0] = np.fromiter((w for w, _ in flat), dtype=np.int32, count=n)
         recs[:, 1] = np.rint(np.fromiter((wd["start"] for _, wd in flat), dtype=np.float64, count=n) * 1000.0).astype(np.int32)
         recs[:, 2] = np.rint(np.fromiter((wd["end"] for _, wd in flat), dtype=np.float64, count=n) * 1000.0).astype(np.int32)
         recs[:, 3] = counts
         recs[:, 4] = np.fromiter((wd["probability"] for _, wd in flat), dtype=np.float32, count=n).view(np.int32)
-        buf[1 + 5 * cap_words:1 + 5 * cap_words + t] = np.fromiter((v for tl in tok_lists for v in tl), dtype=np.int32, count=t)
+        recs[:, 5] = np.fromiter((wd.get("segment", 0) for _, wd in flat), dtype=np.int32, count=n)
+        buf[1 + REC * cap_words:1 + REC * cap_words + t] = np.fromiter((v for tl in tok_lists for v in tl), dtype=np.int32, count=t)
     buf[0] = n
     return torch.from_numpy(buf)
 
@@ -54,8 +61,9 @@ class GatheredWords(Sequence):
     indexed: at 8 ranks x 120 windows a step gathers ~160 k words, and building every dict on every rank would cost
     ~0.3 s of Python per step for results most ranks never look at."""
 
-    def __init__(self, bufs: Sequence[torch.Tensor], n_windows_total: int, cap_words: int):
+    def __init__(self, bufs: Sequence[torch.Tensor], n_windows_total: int, cap_words: int, tokenizer=None):
         self._n = n_windows_total
+        self._tk = tokenizer                               # given: every word dict also carries its decoded text ("word")
         self._parts = []                                   # (recs [n,5], token array, token end offsets)
         first = np.full(n_windows_total + 1, -1, dtype=np.int64)
         self._where = {}                                   # window -> (part index, first record, n records)
@@ -65,9 +73,9 @@ class GatheredWords(Sequence):
             n = int(a[0])
             if n == 0:
                 continue
-            recs = a[1:1 + 5 * n].reshape(n, 5)
+            recs = a[1:1 + REC * n].reshape(n, REC)
             ends = np.cumsum(recs[:, 3], dtype=np.int64)
-            toks = a[1 + 5 * cap_words:1 + 5 * cap_words + int(ends[-1])]
+            toks = a[1 + REC * cap_words:1 + REC * cap_words + int(ends[-1])]
             pi = len(self._parts)
             self._parts.append((recs, toks, ends))
             wins, starts, counts = np.unique(recs[:, 0], return_index=True, return_counts=True)   # records are window-sorted
@@ -97,17 +105,40 @@ class GatheredWords(Sequence):
         tl = toks[lo[0]:hi[-1]].tolist()
         base = lo[0]
         probs = np.ascontiguousarray(r[:, 4]).view(np.float32).astype(np.float64).tolist()
-        return [dict(start=s0, end=e0, tokens=tl[a0 - base:a1 - base], probability=p)
-                for s0, e0, p, a0, a1 in zip((r[:, 1] / 1000.0).tolist(), (r[:, 2] / 1000.0).tolist(), probs, lo, hi)]
+        out = [dict(start=s0, end=e0, tokens=tl[a0 - base:a1 - base], probability=p, segment=sg)
+               for s0, e0, p, sg, a0, a1 in zip((r[:, 1] / 1000.0).tolist(), (r[:, 2] / 1000.0).tolist(), probs, r[:, 5].tolist(),
+                                                lo, hi)]
+        if self._tk is not None:
+            for w in out:
+                w["word"] = self._tk.decode(w["tokens"])
+        return out
 
 
-def unpack_records(bufs: Sequence[torch.Tensor], n_windows_total: int, cap_words: int, lazy: bool = False):
-    g = GatheredWords(bufs, n_windows_total, cap_words)
+def unpack_records(bufs: Sequence[torch.Tensor], n_windows_total: int, cap_words: int, lazy: bool = False, tokenizer=None):
+    g = GatheredWords(bufs, n_windows_total, cap_words, tokenizer=tokenizer)
     return g if lazy else [g[i] for i in range(n_windows_total)]
 
 
+def gathered_to_result(windows: Sequence[List[dict]], tokenizer, language: Optional[str] = None, window_seconds: float = 30.0) -> dict:
+    """Per-window word lists (``GatheredWords`` or plain lists; words carry ``segment`` = index of their segment inside
+    the window) -> dict(text, segments, language) with the keys of ``WhisperResult.to_dict``."""
+    segments = []
+    for wi in range(len(windows)):
+        by_seg = {}
+        for w in windows[wi]:
+            by_seg.setdefault(int(w.get("segment", 0)), []).append(w)
+        for si in sorted(by_seg):
+            ws = [dict(word=w["word"] if "word" in w else tokenizer.decode(w["tokens"]), start=w["start"], end=w["end"],
+                       probability=w["probability"], tokens=list(w["tokens"])) for w in by_seg[si]]
+            segments.append(dict(start=ws[0]["start"], end=ws[-1]["end"], text="".join(w["word"] for w in ws),
+                                 seek=round(wi * window_seconds, 3), tokens=[t for w in ws for t in w["tokens"]], temperature=0.0,
+                                 avg_logprob=None, compression_ratio=None, no_speech_prob=None, words=ws, id=len(segments)))
+    return dict(text="".join(s["text"] for s in segments), segments=segments,
+                language=language or getattr(tokenizer, "language", None))
+
+
 def run_sharded(process: Callable[[int, int], List[List[dict]]], n_windows_total: int, *, device: Optional[torch.device] = None,
-                group=None, lazy: bool = False):
+                group=None, lazy: bool = False, tokenizer=None):
     """``process(lo, hi)`` computes the word lists of windows [lo, hi) on this rank; every rank returns the merged
     result for all windows (``lazy=True``: a ``GatheredWords`` view that builds a window's dicts on access).  The only
     collective is one all_gather of the record buffer."""
@@ -122,7 +153,7 @@ def run_sharded(process: Callable[[int, int], List[List[dict]]], n_windows_total
         buf = buf.to(device)
     gathered = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(gathered, buf, group=group)
-    return unpack_records(gathered, n_windows_total, cap_w, lazy=lazy)
+    return unpack_records(gathered, n_windows_total, cap_w, lazy=lazy, tokenizer=tokenizer)
 
 
 def align_sharded(model, tokenizer, audios: Sequence[torch.Tensor], word_tokens: Sequence[List[List[int]]], group=None):
@@ -135,3 +166,27 @@ def align_sharded(model, tokenizer, audios: Sequence[torch.Tensor], word_tokens:
         return align_words_batch(model, tokenizer, list(audios[lo:hi]), list(word_tokens[lo:hi]))
 
     return run_sharded(process, len(audios), device=model.device, group=group)
+
+
+def transcribe_sharded(model, tokenizer, audio: torch.Tensor, *, group=None, **kw):
+    """Data-parallel transcription of one long 16 kHz waveform (every rank holds it): 30 s shards are split into contiguous
+    ranges per rank, each rank walks its shards with ``transcribe.transcribe``, ONE all_gather of word records, and every rank
+    rebuilds the full result (BASELINE config 4: 8 h over 8 GPUs).  -> WhisperResult (result.make_result)."""
+    from .result import make_result
+    from .transcribe import N_SAMPLES, transcribe
+    audio = audio.detach().float().flatten()
+    n_win = max(1, -(-int(audio.numel()) // N_SAMPLES))
+
+    def process(lo, hi):
+        if hi <= lo:
+            return []
+        d = transcribe(model, tokenizer, audio[lo * N_SAMPLES: hi * N_SAMPLES], **kw)
+        out = [[] for _ in range(hi - lo)]
+        for si, seg in enumerate(d["segments"]):
+            wi = min(int(seg["seek"] // 30.0), hi - lo - 1)
+            for w in seg.get("words") or []:
+                out[wi].append(dict(w, start=w["start"] + lo * 30.0, end=w["end"] + lo * 30.0, segment=si))
+        return out
+
+    words = run_sharded(process, n_win, device=model.device, group=group, tokenizer=tokenizer)
+    return make_result(gathered_to_result(words, tokenizer, getattr(tokenizer, "language", None)))
