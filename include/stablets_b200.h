@@ -262,6 +262,17 @@ STB_API size_t stb_decode_state_bytes(const stb_model* m, int B);
 STB_API size_t stb_decode_ws_bytes(const stb_model* m, int B);
 STB_API int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const void* cross_kv, void* state,
                     float* logits_out, long long ld_logits, void* ws, size_t ws_bytes, void* stream);
+/* The same step for a batch whose INITIAL tokens differ in length (per-window prompts: `decode_options["prompt"] =
+ *    all_tokens[prompt_reset_since:]`, original_whisper.py:533; whisper DecodingTask._get_initial_tokens).  The sequences are
+ *    RIGHT-aligned on the shared counter: sequence b's first token is fed at pos == seq_off[b] (= longest - own length), its own
+ *    position (positional embedding row) is pos - seq_off[b], and its self-attention reads cache rows [seq_off[b], pos] only, so
+ *    every sequence samples its first token at the same step.  Steps with pos < seq_off[b] are idle for b (any token id).
+ *    cache_rows: rows per sequence of the K/V caches, n_text_ctx <= cache_rows <= 2 n_text_ctx (stb_decode_state_bytes_rows).
+ *    seq_off == NULL and cache_rows == n_text_ctx is stb_decode_step. */
+STB_API size_t stb_decode_state_bytes_rows(const stb_model* m, int B, int cache_rows);
+STB_API int stb_decode_step_ragged(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const int32_t* seq_off,
+                           int cache_rows, const void* cross_kv, void* state, float* logits_out, long long ld_logits, void* ws,
+                           size_t ws_bytes, void* stream);
 
 /* per-sequence sampling state kept on the device */
 typedef struct {
@@ -286,6 +297,19 @@ STB_API int stb_sample_greedy(float* logits, long long ld, int B, int V, int eot
                       const uint8_t* suppress_mask, const uint8_t* first_step_mask, const uint8_t* ts_mask,
                       long long ts_mask_stride, int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
                       int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows, void* stream);
+/* stb_sample_greedy plus the temperature > 0 branch of whisper's GreedyDecoder.update (`Categorical(logits=logits /
+ *   temperature).sample()`, used by the temperature fallback of original_whisper.py:349-393):
+ *   temperature > 0: the token is drawn by inverse CDF from p_i ~ exp((l_i - max) / temperature) over the FILTERED logits -- the
+ *   first index whose running sum (index order) exceeds uniform_table[n_sampled][b] * total; uniform_table [table_rows][B] fp32
+ *   in [0, 1) is the caller's random stream (torch.rand under the caller's generator: the draw is a pure function of it).
+ *   sum_logprob accumulates log_softmax(unscaled logits)[drawn token], as the reference does.  temperature == 0: the argmax.
+ *   sample_cap (nullable) [B]: a sequence that has sampled sample_cap[b] tokens is treated as ended (EOT from then on, no
+ *   log-prob) -- the per-sequence form of the reference's `tokens.shape[-1] > n_ctx` stop when initial tokens are ragged. */
+STB_API int stb_sample(float* logits, long long ld, int B, int V, int eot, int ts_begin, int no_timestamps,
+               const uint8_t* suppress_mask, const uint8_t* first_step_mask, const uint8_t* ts_mask, long long ts_mask_stride,
+               int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states, int32_t* next_out,
+               int32_t* token_table, int32_t* argmax_table, int table_rows, float temperature, const float* uniform_table,
+               const int32_t* sample_cap, void* stream);
 
 #ifdef __cplusplus
 }

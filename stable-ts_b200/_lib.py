@@ -80,6 +80,12 @@ _SIGS = {
                                 c_size_t, c_void_p]),
     "stb_sample_greedy": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                   c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "stb_decode_state_bytes_rows": (c_size_t, [c_void_p, c_int, c_int]),
+    "stb_decode_step_ragged": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                       c_longlong, c_void_p, c_size_t, c_void_p]),
+    "stb_sample": (c_int, [c_void_p, c_longlong, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                           c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                           c_void_p, c_void_p]),
     "stb_qkpost_dynamic_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "stb_qk_postprocess_dynamic": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_float, c_int, c_int,
                                            c_void_p, c_int, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p]),
@@ -149,3 +155,11 @@ def prof_report() -> dict:
     buf = ctypes.create_string_buffer(1 << 16)
     check(lib().stb_prof_report(buf, len(buf)))
     return json.loads(buf.value.decode())
+
+
+def device_ctx(device):
+    """``torch.cuda.device(device)`` for a CUDA device; a no-op context for anything else (the CPU stand-in of the tests)."""
+    import contextlib
+    import torch
+    device = torch.device(device)
+    return torch.cuda.device(device) if device.type == "cuda" else contextlib.nullcontext()

@@ -220,21 +220,25 @@ def _set_language(result, tokenizer, language):
 
 def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, task: str = "transcribe", word_timestamps: bool = True,
                regroup=True, suppress_ts_tokens: bool = False, q_levels: int = 20, k_size: int = 5,
-               no_speech_threshold: Optional[float] = 0.6, logprob_threshold: Optional[float] = -1.0,
-               max_instant_words: Optional[float] = 0.5, gap_padding: str = " ...", min_word_dur: float = 0.1,
-               batch_windows: int = 16, shard_seconds: Optional[float] = 30.0, tokenizer=None, temperature=0.0, **decode_options):
-    """``model.transcribe`` (transcribe_stable, original_whisper.py:27-78): -> WhisperResult.  Greedy (temperature 0) decode
-    of static 30 s shards batched ``batch_windows`` at a time (transcribe.py); ``shard_seconds=None`` walks the audio as one
-    sequential shard like the reference (without prompt carry-over)."""
+               temperature: Union[float, Tuple[float, ...]] = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0),
+               compression_ratio_threshold: Optional[float] = 2.4, no_speech_threshold: Optional[float] = 0.6,
+               logprob_threshold: Optional[float] = -1.0, condition_on_previous_text: bool = True,
+               initial_prompt: Optional[str] = None, max_instant_words: Optional[float] = 0.5, gap_padding: str = " ...",
+               min_word_dur: float = 0.1, batch_windows: int = 16, shard_seconds: Optional[float] = 30.0, tokenizer=None,
+               generator: Optional[torch.Generator] = None, uniforms=None, **decode_options):
+    """``model.transcribe`` (transcribe_stable, original_whisper.py:27-78): -> WhisperResult.  Static 30 s shards batched
+    ``batch_windows`` at a time (transcribe.py); ``shard_seconds=None`` walks the audio as one sequential shard like the
+    reference.  Decoding defaults are the reference's: the temperature fallback sequence with its compression-ratio /
+    log-prob / no-speech tests, ``best_of`` draws at temperature > 0, the previous window's text as the prompt of the next
+    (inside a shard).  ``generator`` / ``uniforms``: random stream of the temperature > 0 passes (decode.decode_with_fallback).
+    Beam search is not implemented."""
     from .decode import DecodingOptions
     from .tokenizer import get_tokenizer
     from .transcribe import transcribe as run
-    t0 = temperature[0] if isinstance(temperature, (tuple, list)) else temperature
-    if t0 not in (0, 0.0, None):
-        raise NotImplementedError("B200 transcribe: temperature > 0 sampling is not implemented (greedy only)")
-    for k in ("condition_on_previous_text", "initial_prompt", "prompt", "prefix"):
-        if decode_options.pop(k, None) not in (None, False, "", []):
-            raise NotImplementedError(f"B200 transcribe: {k} is not implemented (shards are independent)")
+    if decode_options.get("beam_size") is not None:
+        raise NotImplementedError("B200 transcribe: beam search is not implemented (greedy / temperature sampling only)")
+    if decode_options.pop("prompt", None):
+        raise TypeError("transcribe: use initial_prompt (the per-window prompt is managed by condition_on_previous_text)")
     wave = _as_waveform(audio, model)
     if language is None:
         language = "en" if not model.is_multilingual else model.detect_language_of(wave[:480000])
@@ -244,7 +248,9 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
     d = run(model, tk, wave, batch_windows=batch_windows, shard_seconds=shard_seconds, word_timestamps=word_timestamps,
             options=opts, suppress_ts_tokens=suppress_ts_tokens, q_levels=q_levels, k_size=k_size,
             no_speech_threshold=no_speech_threshold, logprob_threshold=logprob_threshold, max_instant_words=max_instant_words,
-            gap_padding=gap_padding, min_word_dur=min_word_dur)
+            gap_padding=gap_padding, min_word_dur=min_word_dur, temperature=temperature,
+            compression_ratio_threshold=compression_ratio_threshold, condition_on_previous_text=condition_on_previous_text,
+            initial_prompt=initial_prompt, generator=generator, uniforms=uniforms)
     d["language"] = language
     res = make_result(d)
     if regroup and hasattr(res, "regroup") and word_timestamps:

@@ -25,8 +25,8 @@ namespace stb {
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, float* __restrict__ Vc, int d, int ctx,
-                        const int32_t* __restrict__ pos_ptr, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                        float* __restrict__ out_f32) {
+                        const int32_t* __restrict__ pos_ptr, const int32_t* __restrict__ seq_off, __half* __restrict__ out_hi,
+                        __half* __restrict__ out_lo, float* __restrict__ out_f32) {
     __shared__ float s_m[4][4], s_l[4][4];
     __shared__ float s_acc[4][4][64];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
@@ -36,6 +36,9 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
     pdl_wait();
     const int pos = *pos_ptr;
     const int n = pos + 1;
+    // ragged initial tokens (prompts of different lengths in one batch) are RIGHT-aligned on the shared position counter:
+    // sequence b's own tokens occupy cache rows [seq_off[b], pos]; earlier rows hold idle steps and are never attended
+    const int first_row = seq_off != nullptr ? min(seq_off[b], pos) : 0;
     const float* row = qkv + (long long)b * 3 * d;
     float* kc = Kc + (long long)b * ctx * d + h * 64;
     float* vc = Vc + (long long)b * ctx * d + h * 64;
@@ -48,7 +51,7 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int base = 0; base < n; base += 64) {               // block-uniform trip count: 64 keys per CTA iteration
+    for (int base = first_row; base < n; base += 64) {       // block-uniform trip count: 64 keys per CTA iteration
         const int j0 = base + w * 4 + grp;
         float4 ka[4], kb[4], va[4], vb[4];
 #pragma unroll
@@ -454,12 +457,15 @@ __global__ void __launch_bounds__(256) v_headmajor_kernel(const __half* __restri
     }
 }
 
-__global__ void embed_step_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ pos_ptr, int d,
-                                  const float* __restrict__ emb, const float* __restrict__ posemb, float* __restrict__ x) {
+__global__ void embed_step_kernel(const int32_t* __restrict__ tokens, const int32_t* __restrict__ pos_ptr,
+                                  const int32_t* __restrict__ seq_off, int n_pos, int d, const float* __restrict__ emb,
+                                  const float* __restrict__ posemb, float* __restrict__ x) {
     const int b = blockIdx.x;
     pdl_trigger();
     pdl_wait();
-    const int pos = *pos_ptr;
+    int pos = *pos_ptr;
+    if (seq_off != nullptr) pos = max(pos - seq_off[b], 0);  // the sequence's own position (idle steps before it: row 0)
+    pos = min(pos, n_pos - 1);                               // a sequence past its n_ctx stop idles on the last row
     const float4* e = reinterpret_cast<const float4*>(emb + (long long)tokens[b] * d);
     const float4* p = reinterpret_cast<const float4*>(posemb + (long long)pos * d);
     float4* o = reinterpret_cast<float4*>(x + (long long)b * d);
@@ -502,7 +508,8 @@ sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, i
                      const uint8_t* __restrict__ ts_mask, long long ts_mask_stride, int max_initial_ts, int apply_ts_rules,
                      const int32_t* __restrict__ forced_table, stb_seq_state* __restrict__ states,
                      int32_t* __restrict__ next_out, int32_t* __restrict__ token_table, int32_t* __restrict__ argmax_table,
-                     int table_rows) {
+                     int table_rows, float temperature, const float* __restrict__ uniform_table,
+                     const int32_t* __restrict__ sample_cap) {
     __shared__ BlockRed red;
     const int b = blockIdx.x;
     pdl_trigger();
@@ -575,18 +582,67 @@ sample_greedy_kernel(float* __restrict__ logits, long long ld, int V, int eot, i
     __syncthreads();
     if ((threadIdx.x & 31) == 0) red.i[threadIdx.x >> 5] = arg;
     __syncthreads();
+    // ---- temperature > 0 (GreedyDecoder.update: Categorical(logits / T).sample()): inverse-CDF draw from
+    // p_i ~ exp((l_i - max) / T) with the caller's uniform u in [0, 1) for this (step, sequence): the first index whose
+    // running sum exceeds u * total.  Every thread owns a CONTIGUOUS index range, so the block scan follows index order.
+    int pick = 0x7fffffff;
+    if (temperature > 0.f && uniform_table != nullptr && st.n_sampled < table_rows) {
+        // running sums in fp64: a token's share (~1e-5 of the total for flat distributions) must stay far above the
+        // rounding of the sum, or the draw would depend on the summation order
+        __shared__ double dsum[32];
+        const float inv_t = 1.f / temperature;
+        const int chunk = (V + (int)blockDim.x - 1) / (int)blockDim.x;
+        const int i0 = min((int)threadIdx.x * chunk, V), i1 = min(i0 + chunk, V);
+        double cs = 0.0;
+        for (int i = i0; i < i1; ++i) cs += (double)expf((l[i] - gmax) * inv_t);
+        double inc = cs;                                      // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)(threadIdx.x & 31) >= o) inc += v;
+        }
+        if ((threadIdx.x & 31) == 31) dsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        double before = 0.0, total = 0.0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+            if (k < (int)(threadIdx.x >> 5)) before += dsum[k];
+            total += dsum[k];
+        }
+        const double target = (double)uniform_table[(long long)st.n_sampled * gridDim.x + b] * total;
+        double run = before + (inc - cs);                     // sum of everything before this thread's range
+        if (target < run + cs) {
+            for (int i = i0; i < i1; ++i) {
+                run += (double)expf((l[i] - gmax) * inv_t);
+                if (run > target) { pick = i; break; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pick = min(pick, __shfl_xor_sync(0xffffffffu, pick, o));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red.f[threadIdx.x >> 5] = __int_as_float(pick);
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
         int a = red.i[0];
         for (int k = 1; k < (int)(blockDim.x >> 5); ++k) a = min(a, red.i[k]);
+        int drawn = a;                                        // temperature 0: the argmax
+        if (temperature > 0.f && uniform_table != nullptr && st.n_sampled < table_rows) {
+            int pk = 0x7fffffff;
+            for (int k = 0; k < (int)(blockDim.x >> 5); ++k) pk = min(pk, __float_as_int(red.f[k]));
+            if (pk < V) drawn = pk;                           // (rounding left u * total >= every running sum: keep the argmax)
+        }
         const float log_s = logf(s);                          // lse = gmax + log_s; kept apart: gmax may be -FLT_MAX
-        const bool was_done = st.n_sampled >= 1 && st.last_tok == eot;
-        int next = a;
+        // ended: EOT sampled earlier, or the per-sequence cap reached (the reference's `tokens.shape[-1] > n_ctx` stop for a
+        // sequence whose initial tokens are longer than its neighbours')
+        const bool was_done = (st.n_sampled >= 1 && st.last_tok == eot) || (sample_cap != nullptr && st.n_sampled >= sample_cap[b]);
+        int next = drawn;
         const int B = gridDim.x;
         const bool in_table = st.n_sampled < table_rows;
         if (argmax_table && in_table) argmax_table[(long long)st.n_sampled * B + b] = a;
-        // GreedyDecoder.update accumulates the log-prob of ITS pick (the argmax); a forced script (benchmarks, tests) only
-        // replaces the token that is appended afterwards, exactly as oracle/stable_path.py:decode_window does
-        const float lp = (l[a] - gmax) - log_s;
+        // GreedyDecoder.update accumulates the log-prob (log_softmax of the UNSCALED logits) of ITS pick (the argmax, or the
+        // draw at temperature > 0); a forced script (benchmarks, tests) only replaces the token that is appended afterwards,
+        // exactly as oracle/stable_path.py:decode_window does
+        const float lp = (l[drawn] - gmax) - log_s;
         if (forced_table && in_table) next = forced_table[(long long)st.n_sampled * B + b];
         if (!was_done) st.sum_logprob += lp;
         if (was_done) next = eot;                           // finished rows keep emitting EOT
@@ -609,25 +665,37 @@ __global__ void bump_pos_kernel(int32_t* pos) {
 
 }  // namespace stb
 
-extern "C" int stb_sample_greedy(float* logits, long long ld, int B, int V, int eot, int ts_begin, int no_timestamps,
-                                 const uint8_t* suppress_mask, const uint8_t* first_step_mask, const uint8_t* ts_mask,
-                                 long long ts_mask_stride, int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
-                                 int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows, void* stream) {
-    STB_REQUIRE(logits && states && next_out && B >= 1 && V >= 1 && ld >= V, "stb_sample_greedy: bad arguments");
-    STB_REQUIRE(ts_mask_stride == 0 || ts_mask_stride >= 1501, "stb_sample_greedy: ts_mask_stride must be 0 (shared) or >= 1501");
+extern "C" int stb_sample(float* logits, long long ld, int B, int V, int eot, int ts_begin, int no_timestamps,
+                          const uint8_t* suppress_mask, const uint8_t* first_step_mask, const uint8_t* ts_mask,
+                          long long ts_mask_stride, int max_initial_ts, int apply_ts_rules, const int32_t* forced_table,
+                          stb_seq_state* states, int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows,
+                          float temperature, const float* uniform_table, const int32_t* sample_cap, void* stream) {
+    STB_REQUIRE(logits && states && next_out && B >= 1 && V >= 1 && ld >= V, "stb_sample: bad arguments");
+    STB_REQUIRE(ts_mask_stride == 0 || ts_mask_stride >= 1501, "stb_sample: ts_mask_stride must be 0 (shared) or >= 1501");
+    STB_REQUIRE(temperature >= 0.f && (temperature == 0.f || uniform_table != nullptr),
+                "stb_sample: temperature > 0 needs the table of uniform draws [table_rows][B]");
     stb::ProfScope ps("sample_greedy", (cudaStream_t)stream, (double)B * V * 4.0 * 3);
     STB_CUDA_OK(stb::launch_pdl(stb::sample_greedy_kernel, dim3(B), dim3(1024), 0, (cudaStream_t)stream, logits, ld, V, eot, ts_begin,
                                 no_timestamps, suppress_mask, first_step_mask, ts_mask, ts_mask_stride, max_initial_ts, apply_ts_rules, forced_table,
-                                states, next_out, token_table, argmax_table, table_rows));
+                                states, next_out, token_table, argmax_table, table_rows, temperature, uniform_table, sample_cap));
     STB_LAUNCH_OK();
     return STB_OK;
 }
 
+extern "C" int stb_sample_greedy(float* logits, long long ld, int B, int V, int eot, int ts_begin, int no_timestamps,
+                                 const uint8_t* suppress_mask, const uint8_t* first_step_mask, const uint8_t* ts_mask,
+                                 long long ts_mask_stride, int max_initial_ts, int apply_ts_rules, const int32_t* forced_table, stb_seq_state* states,
+                                 int32_t* next_out, int32_t* token_table, int32_t* argmax_table, int table_rows, void* stream) {
+    return stb_sample(logits, ld, B, V, eot, ts_begin, no_timestamps, suppress_mask, first_step_mask, ts_mask, ts_mask_stride,
+                      max_initial_ts, apply_ts_rules, forced_table, states, next_out, token_table, argmax_table, table_rows, 0.f,
+                      nullptr, nullptr, stream);
+}
+
 namespace stb {
-int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
-                     __half* ol, float* of, cudaStream_t st) {
+int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos,
+                     const int32_t* seq_off, __half* oh, __half* ol, float* of, cudaStream_t st) {
     ProfScope ps("decode_self_attn", st);
-    STB_CUDA_OK(launch_pdl(decode_self_attn_kernel, dim3(H, B), dim3(128), 0, st, qkv, Kc, Vc, d, ctx, pos, oh, ol, of));
+    STB_CUDA_OK(launch_pdl(decode_self_attn_kernel, dim3(H, B), dim3(128), 0, st, qkv, Kc, Vc, d, ctx, pos, seq_off, oh, ol, of));
     STB_LAUNCH_OK();
     return STB_OK;
 }
@@ -670,9 +738,9 @@ int v_headmajor(const __half* vT_hi, int BH, int T, int Tp, __half* v_hi, cudaSt
     STB_LAUNCH_OK();
     return STB_OK;
 }
-int embed_step(const int32_t* tokens, const int32_t* pos, int B, int d, const float* emb, const float* posemb, float* x,
-               cudaStream_t st) {
-    STB_CUDA_OK(launch_pdl(embed_step_kernel, dim3(B), dim3(128), 0, st, tokens, pos, d, emb, posemb, x));
+int embed_step(const int32_t* tokens, const int32_t* pos, const int32_t* seq_off, int n_pos, int B, int d, const float* emb,
+               const float* posemb, float* x, cudaStream_t st) {
+    STB_CUDA_OK(launch_pdl(embed_step_kernel, dim3(B), dim3(128), 0, st, tokens, pos, seq_off, n_pos, d, emb, posemb, x));
     STB_LAUNCH_OK();
     return STB_OK;
 }

@@ -437,18 +437,20 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.bytes = c.off;
     return w;
 }
-static size_t decode_state_bytes(const stb_model* m, int B) {
-    return (size_t)m->dims.n_text_layer * 2 * B * m->dims.n_text_ctx * m->dims.n_text_state * sizeof(float);
+static size_t decode_state_bytes(const stb_model* m, int B, int cache_rows) {
+    return (size_t)m->dims.n_text_layer * 2 * B * cache_rows * m->dims.n_text_state * sizeof(float);
 }
 
-static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos, const void* ckv, void* state, float* logits,
-                       long long ld_logits, void* ws, cudaStream_t st) {
+// seq_off (nullable) [B]: first cache row of each sequence; cache_rows: rows per sequence of the K/V caches (>= n_text_ctx
+// when ragged initial tokens are right-aligned, so that the shortest sequence still reaches its own n_text_ctx positions)
+static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos, const int32_t* seq_off, int cache_rows,
+                       const void* ckv, void* state, float* logits, long long ld_logits, void* ws, cudaStream_t st) {
     const stb_dims& D = m->dims;
-    const int d = D.n_text_state, H = D.n_text_head, ctx = D.n_text_ctx;
+    const int d = D.n_text_state, H = D.n_text_head, ctx = cache_rows;
     const void* const(*t)[2] = m->t;
     StepWs w = carve_step(m, B, ws);
     const size_t cache = (size_t)B * ctx * d;
-    STB_TRY(embed_step(tokens, pos, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
+    STB_TRY(embed_step(tokens, pos, seq_off, D.n_text_ctx, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
     const void* emb_hi = t[STB_T_DEC_TOKEMB][0];
     const void* emb_lo = m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr;
     // Linear layers of the step, by batch size:
@@ -526,7 +528,7 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
         // w.ln holds attn_ln(x) here (previous layer's fc2 finish, or the standalone LayerNorm above)
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_QKV_W), W_LO(L, STB_L_QKV_W), 3 * d, W_F32(L, STB_L_QKV_B), STB_ACT_NONE, nullptr,
                     w.qkv, none, 3 * d, nullptr, nullptr));
-        STB_TRY(decode_attn_self(w.qkv, Kc, Vc, B, H, d, ctx, pos, w.attn.hi, w.attn.lo, nullptr, st));
+        STB_TRY(decode_attn_self(w.qkv, Kc, Vc, B, H, d, ctx, pos, seq_off, w.attn.hi, w.attn.lo, nullptr, st));
         STB_TRY(lin(w.attn, d, W_HI(L, STB_L_OUT_W), W_LO(L, STB_L_OUT_W), d, W_F32(L, STB_L_OUT_B), STB_ACT_NONE, w.x, w.x,
                     none, d, W_F32(L, STB_L_CROSS_LN_G), W_F32(L, STB_L_CROSS_LN_B)));
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_CQ_W), W_LO(L, STB_L_CQ_W), d, W_F32(L, STB_L_CQ_B), STB_ACT_NONE, nullptr, w.q,
@@ -671,15 +673,28 @@ extern "C" int stb_decoder_forward(stb_model* m, const int32_t* tokens, int B, i
     return stb::decoder_forward(m, tokens, B, M, cross_kv, logits, ld_logits, qk_out, sel_pairs_host, n_sel, ws, (cudaStream_t)stream);
 }
 
-extern "C" size_t stb_decode_state_bytes(const stb_model* m, int B) { return m ? stb::decode_state_bytes(m, B) : 0; }
+extern "C" size_t stb_decode_state_bytes(const stb_model* m, int B) { return m ? stb::decode_state_bytes(m, B, m->dims.n_text_ctx) : 0; }
+extern "C" size_t stb_decode_state_bytes_rows(const stb_model* m, int B, int cache_rows) {
+    return m && cache_rows >= 1 ? stb::decode_state_bytes(m, B, cache_rows) : 0;
+}
 extern "C" size_t stb_decode_ws_bytes(const stb_model* m, int B) { return m ? stb::carve_step(m, B, nullptr).bytes : 0; }
 
-extern "C" int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const void* cross_kv, void* state,
-                               float* logits_out, long long ld_logits, void* ws, size_t ws_bytes, void* stream) {
+extern "C" int stb_decode_step_ragged(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const int32_t* seq_off,
+                                      int cache_rows, const void* cross_kv, void* state, float* logits_out, long long ld_logits,
+                                      void* ws, size_t ws_bytes, void* stream) {
     STB_REQUIRE(m && tokens_in && pos && cross_kv && state && logits_out && ws && B >= 1, "stb_decode_step: bad arguments");
     STB_REQUIRE(ld_logits >= m->dims.n_vocab && ld_logits % 4 == 0, "stb_decode_step: ld_logits must be >= n_vocab and a multiple of 4");
     STB_REQUIRE(m->dims.n_text_ctx <= 448, "stb_decode_step: n_text_ctx > 448 unsupported");
+    STB_REQUIRE(cache_rows >= m->dims.n_text_ctx && cache_rows <= 2 * m->dims.n_text_ctx,
+                "stb_decode_step: cache_rows must be in [n_text_ctx, 2 n_text_ctx]");
     STB_TRY(check_weights(m, false, true));
     STB_REQUIRE(ws_bytes >= stb_decode_ws_bytes(m, B), "stb_decode_step: workspace too small");
-    return stb::decode_step(m, tokens_in, B, pos, cross_kv, state, logits_out, ld_logits, ws, (cudaStream_t)stream);
+    return stb::decode_step(m, tokens_in, B, pos, seq_off, cache_rows, cross_kv, state, logits_out, ld_logits, ws, (cudaStream_t)stream);
+}
+
+extern "C" int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const void* cross_kv, void* state,
+                               float* logits_out, long long ld_logits, void* ws, size_t ws_bytes, void* stream) {
+    STB_REQUIRE(m, "stb_decode_step: bad arguments");
+    return stb_decode_step_ragged(m, tokens_in, B, pos, nullptr, m->dims.n_text_ctx, cross_kv, state, logits_out, ld_logits, ws,
+                                  ws_bytes, stream);
 }

@@ -35,8 +35,9 @@ int im2col3(const __half* src, int B, int C, int Tin_pad, int Tout, int stride, 
 int capture_heads(const float* S, int B, int H, int M, long long ld, float* out, int n_sel, const CaptureList& list,
                   cudaStream_t st);
 
-int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos, __half* oh,
-                     __half* ol, float* of, cudaStream_t st);
+// seq_off (nullable) [B]: first cache row of each sequence (ragged initial tokens right-aligned on the shared counter)
+int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos,
+                     const int32_t* seq_off, __half* oh, __half* ol, float* of, cudaStream_t st);
 // decode-step view of one layer's cross K / V: fp16 planes, head-major [B][H][T][64] (K is the GEMM hi plane itself)
 struct CrossDecodeKV {
     const __half* k_hi;
@@ -59,8 +60,8 @@ int decode_linear(const void* x_hi, const void* x_lo, int B, int k, const void* 
                   int act, const float* res, long long ld_res, float* out_f32, void* out_hi, void* out_lo, long long ld_out,
                   cudaStream_t st);
 int decode_linear_split(int n, int k);
-int embed_step(const int32_t* tokens, const int32_t* pos, int B, int d, const float* emb, const float* posemb, float* x,
-               cudaStream_t st);
+int embed_step(const int32_t* tokens, const int32_t* pos, const int32_t* seq_off, int n_pos, int B, int d, const float* emb,
+               const float* posemb, float* x, cudaStream_t st);
 int bump_pos(int32_t* pos, cudaStream_t st);
 
 }  // namespace stb

@@ -11,15 +11,20 @@ Mirrored per-window behaviour: non-VAD silence masks -> ``ts_token_mask`` per wi
 original_whisper.py:504-511), silent-window skip (:508-510), the no-speech / log-prob window skip (:537-547), segment
 pruning (:604-627), ``max_instant_words`` (:655-663) and the data-dependent seek (:703-710; ``transcribe`` walks every
 shard until its end, so speech after the last closed segment of a window is re-decoded exactly as the reference does).
+Temperature fallback (``decode_with_fallback``, :349-393) runs batched: only the windows that fail the compression-ratio /
+log-prob test are decoded again at the next temperature.  Prompt conditioning (``condition_on_previous_text`` /
+``initial_prompt``, :320-323,533,696-698) is carried per shard; windows with prompts of different lengths share a batch
+(right-aligned initial tokens, stb_decode_step_ragged).
 Out of scope here (reference control plane): VAD models, word-level ``suppress_silence`` re-timing
-(result.py), temperature fallback, prompt conditioning, language detection, regrouping.
+(result.py), regrouping.
 """
 from typing import List, Optional, Sequence
 
 import numpy as np
 import torch
 
-from .decode import DecodingOptions, decode_windows
+from ._lib import device_ctx
+from .decode import DecodingOptions, decode_with_fallback
 from .model import B200Whisper
 from .timing import add_word_timestamps_batch
 
@@ -73,7 +78,9 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                        enc: Optional[dict] = None, n_samples: Optional[Sequence[int]] = None, use_graph: bool = True,
                        suppress_ts_tokens: bool = False, skip_silent: bool = False, q_levels: int = 20, k_size: int = 5,
                        no_speech_threshold: Optional[float] = None, logprob_threshold: Optional[float] = None,
-                       max_instant_words: Optional[float] = None):
+                       max_instant_words: Optional[float] = None, temperature=0.0,
+                       compression_ratio_threshold: Optional[float] = None, prompts=None,
+                       generator: Optional[torch.Generator] = None, uniforms=None):
     """B independent <=30 s windows -> (list (per window) of segment dicts with ``words``, info).
     ``enc`` (+ ``n_samples``) may be passed instead of ``audios`` when the encoder output is already on the device.
 
@@ -81,6 +88,9 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
     feeds one ``ts_token_mask`` row per window to the sampler, the latter drops windows that are entirely silent.
     no_speech_threshold / logprob_threshold / max_instant_words: the reference's per-window filters (transcribe_stable
     defaults 0.6 / -1.0 / 0.5); None here = off, so that fixed-script benchmark windows are never dropped.
+    temperature (a number or the fallback sequence) / compression_ratio_threshold / logprob_threshold / no_speech_threshold:
+    ``decode_with_fallback`` (original_whisper.py:349-393); prompts: per-window previous-context tokens (:533);
+    generator / uniforms: the random stream of the temperature > 0 passes (decode.decode_windows).
     info["advance"][b]: samples the reference's seek would move by after this window (original_whisper.py:703-710)."""
     dev_audio = None
     if enc is None:
@@ -96,9 +106,9 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                 a = a.detach().float().flatten()[:N_SAMPLES]
                 batch[i, : a.numel()] = a
                 n_samples.append(int(a.numel()))
-        if batch.device.type == "cpu" and not batch.is_pinned():
+        if batch.device.type == "cpu" and torch.device(model.device).type == "cuda" and not batch.is_pinned():
             batch = batch.pin_memory()
-        with torch.cuda.device(model.device):
+        with device_ctx(model.device):
             dev_audio = batch.to(model.device, non_blocking=True)
             mel = model.log_mel(dev_audio)
             enc = model.encode(mel)
@@ -126,8 +136,13 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
             ts_token_mask = masks
     # the cross K/V block and the KV cache live in model-owned buffers: they are consumed inside this call (decode loop, then
     # the alignment pass below) and are by far the largest allocations of a step
-    results, extras = decode_windows(model, tokenizer, enc, options, ts_token_mask=ts_token_mask,
-                                     forced_tokens=forced_tokens, use_graph=use_graph, reuse_buffers=True)
+    results, extras, n_fallback = decode_with_fallback(
+        model, tokenizer, enc, options, temperature=temperature, compression_ratio_threshold=compression_ratio_threshold,
+        logprob_threshold=logprob_threshold, no_speech_threshold=no_speech_threshold, ts_token_mask=ts_token_mask,
+        prompts=prompts, generator=generator, uniforms=uniforms, forced_tokens=forced_tokens, use_graph=use_graph,
+        reuse_buffers=True)
+    # a re-decode of a subset (or a best_of batch) overwrote the model-owned cross K/V block: the alignment pass rebuilds it
+    ckv_valid = not any(n_fallback) and extras.get("n_group", 1) == 1
     windows, advance, skipped = [], [], []
     for b in range(B):
         dur = n_samples[b] / SAMPLE_RATE
@@ -151,8 +166,8 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
         advance.append(n_samples[b] if (skip or single_ending or not len(toks)) else num)
         skipped.append(bool(skip))
     if word_timestamps:
-        add_word_timestamps_batch(windows, model, tokenizer, enc=enc, ckv=extras["ckv"], gap_padding=gap_padding,
-                                  min_word_dur=min_word_dur)
+        add_word_timestamps_batch(windows, model, tokenizer, enc=enc, ckv=extras["ckv"] if ckv_valid else None,
+                                  gap_padding=gap_padding, min_word_dur=min_word_dur)
         if max_instant_words is not None:                          # original_whisper.py:655-663
             for w in windows:
                 w["segments"] = [s for s in w["segments"] if not s["words"] or float(np.mean(np.array(
@@ -166,28 +181,41 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
 
 def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_windows: int = 16, shard_seconds: Optional[float] = 30.0,
                no_speech_threshold: Optional[float] = 0.6, logprob_threshold: Optional[float] = -1.0,
-               max_instant_words: Optional[float] = 0.5, skip_silent: bool = True, **kw) -> dict:
+               max_instant_words: Optional[float] = 0.5, skip_silent: bool = True, condition_on_previous_text: bool = False,
+               initial_prompt: Optional[str] = None, **kw) -> dict:
     """One long audio as static shards (clip boundaries at multiples of ``shard_seconds``, no prompt carry-over: the sharded
     setting of SURVEY.md section 8e).  Inside a shard the walk is the reference's: a window starts at the shard's seek,
     and the seek then moves by the data-dependent amount of original_whisper.py:703-710, so the tail after the last closed
     segment of a window is decoded again by the next window.  Every round batches the current window of up to
     ``batch_windows`` unfinished shards.  ``shard_seconds=None``: the whole audio is one shard (sequential, as the reference).
+    condition_on_previous_text / initial_prompt: the tokens of a shard's kept segments are the prompt of its next window
+    (``all_tokens[prompt_reset_since:]``, original_whisper.py:320-323,533,673-675,696-698), reset after a window decoded at
+    temperature > 0.5; every shard starts from ``initial_prompt``.
     -> dict(text, segments, language) in the shape of WhisperResult.to_dict (result.py:1398-1406)."""
     audio = audio.detach().float().flatten()
     total = int(audio.numel())
     step = total if not shard_seconds else max(int(round(shard_seconds * SAMPLE_RATE)), 1)
     shards = [[lo, min(lo + step, total)] for lo in range(0, max(total, 1), step)]          # [seek, end]
     per_shard = [[] for _ in shards]
+    init = tokenizer.encode(" " + initial_prompt.strip()) if initial_prompt is not None else []
+    all_tokens = [list(init) for _ in shards]
+    reset_since = [0] * len(shards)
+    use_prompts = condition_on_previous_text or bool(init)
     live = [i for i, (lo, hi) in enumerate(shards) if hi > lo]
     while live:
         now, live = live[:batch_windows], live[batch_windows:]
         part = [audio[shards[i][0]: min(shards[i][0] + N_SAMPLES, shards[i][1])] for i in now]
         segs, info = transcribe_windows(model, tokenizer, part, time_offsets=[shards[i][0] / SAMPLE_RATE for i in now],
                                         no_speech_threshold=no_speech_threshold, logprob_threshold=logprob_threshold,
-                                        max_instant_words=max_instant_words, skip_silent=skip_silent, **kw)
+                                        max_instant_words=max_instant_words, skip_silent=skip_silent,
+                                        prompts=[all_tokens[i][reset_since[i]:] for i in now] if use_prompts else None, **kw)
         again = []
         for k, i in enumerate(now):
             per_shard[i].extend(segs[k])
+            if segs[k]:                                       # original_whisper.py:673-675,696-698
+                all_tokens[i].extend(t for s in segs[k] for t in s["tokens"])
+                if not condition_on_previous_text or info["decode"][k].temperature > 0.5:
+                    reset_since[i] = len(all_tokens[i])
             shards[i][0] += max(int(info["advance"][k]), 1)
             if shards[i][0] < shards[i][1]:
                 again.append(i)

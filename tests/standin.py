@@ -111,3 +111,84 @@ class OracleBackedModel(WhisperProtocol):
     def dtw(self, matrix, negate=True, want_path=False):
         assert negate and not want_path
         return torch.from_numpy(np.stack([SP.jumps_from_matrix(m) for m in matrix]).astype(np.int32))
+
+
+class OracleStepEngine:
+    """CPU stand-in for ``stable_ts_b200.decode.StepEngine`` (same attributes and methods), so that the HOST logic of
+    ``decode_windows`` / ``decode_with_fallback`` / ``transcribe`` -- right-aligned ragged prompts, per-sequence caps, best_of
+    grouping, fallback subsets, prompt carry-over -- runs in the build container and can be compared with the unmodified
+    reference.  ``feed`` = the oracle decoder on the sequence's own token history; ``sample`` = the oracle's ApplyTimestampRules
+    + the masks the host built + the update rule of stb_sample (argmax, or inverse CDF of the given uniforms)."""
+
+    def __init__(self, model, B, table_rows, reuse_buffers=False, seq_off=None, cache_rows=None):
+        self.m, self.B, self.rows = model, B, table_rows
+        V = model.dims.n_vocab
+        self.ldv = (V + 7) // 8 * 8
+        self.off = [0] * B if seq_off is None else [int(v) for v in seq_off]
+        self.pos = torch.zeros(1, dtype=torch.int32)
+        self.logits = torch.zeros(B, self.ldv)
+        self.seq = torch.zeros(B, 6, dtype=torch.int32)
+        self.next = torch.zeros(B, dtype=torch.int32)
+        self.tok_table = torch.zeros(table_rows, B, dtype=torch.int32)
+        self.arg_table = torch.zeros(table_rows, B, dtype=torch.int32)
+        self.forced = self.uniform = self.cap = self.graph = None
+        self.temperature = 0.0
+        self.graph_nodes = 0
+        self.hist = [[] for _ in range(B)]
+        self.begin = None
+        self.sum_lp = [0.0] * B
+
+    def reset(self):
+        pass
+
+    @torch.no_grad()
+    def feed(self, tokens, ckv):
+        om, V, p = self.m.om, self.m.dims.n_vocab, int(self.pos)
+        for b in range(self.B):
+            if p < self.off[b]:
+                continue                                   # idle step of a shorter sequence
+            self.hist[b].append(int(tokens[b]))
+            if len(self.hist[b]) <= self.m.dims.n_text_ctx:
+                self.logits[b, :V] = om.decoder(torch.tensor([self.hist[b]]), ckv["f32"][b:b + 1])[0, -1]
+        self.pos += 1
+
+    def sample(self, tk, suppress, first_mask, ts_mask, max_initial_ts, apply_ts_rules):
+        from oracle.whisper_ref.decoding import ApplyTimestampRules
+        V = self.m.dims.n_vocab
+        if self.begin is None:
+            self.begin = [len(h) for h in self.hist]
+        for b in range(self.B):
+            n = len(self.hist[b]) - self.begin[b]
+            lg = self.logits[b:b + 1, :V].clone()
+            toks = torch.tensor([self.hist[b]])
+            if n == 0 and first_mask is not None:
+                lg[:, first_mask.bool()] = -np.inf
+            if suppress is not None:
+                lg[:, suppress.bool()] = -np.inf
+            if apply_ts_rules:
+                ApplyTimestampRules(tk, self.begin[b], max_initial_ts if max_initial_ts >= 0 else None).apply(lg, toks)
+            if ts_mask is not None:
+                row = ts_mask if ts_mask.ndim == 1 else ts_mask[b]
+                lg[:, tk.timestamp_begin:][:, row.bool()] = -np.inf
+            lg.nan_to_num_(-np.inf)
+            arg = int(lg[0].argmax())
+            pick = arg
+            if self.temperature > 0 and n < self.rows:
+                c = torch.softmax(lg[0].double() / self.temperature, -1).cumsum(-1)
+                hit = (c > float(self.uniform[n, b])).nonzero()
+                pick = int(hit[0]) if len(hit) else arg
+            done = (n >= 1 and self.hist[b][-1] == tk.eot) or (self.cap is not None and n >= int(self.cap[b]))
+            nxt = pick
+            if n < self.rows:
+                self.arg_table[n, b] = arg
+                if self.forced is not None:
+                    nxt = int(self.forced[n, b])
+            if not done:
+                self.sum_lp[b] += float(torch.log_softmax(lg[0].float(), -1)[pick])
+            else:
+                nxt = int(tk.eot)
+            if n < self.rows:
+                self.tok_table[n, b] = nxt
+            self.next[b] = nxt
+            self.seq[b, 4] = int(nxt == tk.eot)
+        self.seq[:, 5] = torch.tensor(self.sum_lp, dtype=torch.float32).view(torch.int32)

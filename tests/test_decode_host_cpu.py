@@ -1,0 +1,133 @@
+"""Host logic of the decode / transcribe drivers in the build container (SURVEY.md section 8 rows a9 + b): the batched engine's
+bookkeeping -- right-aligned ragged prompts, per-sequence n_ctx caps, best_of grouping and ranking, temperature-fallback
+subsets, prompt carry-over and reset, data-dependent seek -- over an oracle-backed stand-in for the model AND the step engine
+(tests/standin.py), compared with the UNMODIFIED ``transcribe_stable`` over the same oracle model.  The kernels behind the real
+engine are pinned by tests/test_gpu_sampling.py and tests/test_gpu_boundary.py on the GPU box."""
+import os
+import sys
+
+import pytest
+import torch
+
+REFERENCE = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree only exists in the build container")
+
+
+@pytest.fixture(scope="module")
+def env():
+    import oracle.whisper_ref as W
+    W.install_as_whisper()
+    if REFERENCE not in sys.path:
+        sys.path.insert(0, REFERENCE)
+    import stable_whisper  # noqa: F401
+    from oracle import stable_path as SP
+    from standin import OracleBackedModel, OracleStepEngine
+    from stable_ts_b200 import api
+    from stable_ts_b200.tokenizer import get_tokenizer
+    om = W.build_model("tiny.en", seed=3)
+    stand = OracleBackedModel(om)
+    stand.step_engine_cls = OracleStepEngine
+    stand = api.modify_model(stand)
+    tk = get_tokenizer(stand, language="en", task="transcribe", synthetic=True)
+    # the silence detector's device stage has no CPU path in the product: stand in with the oracle's restatement (the kernel
+    # itself is pinned bit-exactly by tests/test_gpu_silence.py)
+    import numpy as np
+    import stable_ts_b200.silence as sil
+    from oracle import silence as SIL
+
+    def sound_masks(audio, q_levels=20, k_size=5, want_loudness=False):
+        audio = audio[None] if audio.ndim == 1 else audio
+        if round(audio.shape[1] / 320) + 1 <= 2:
+            return None, None
+        loud = [SIL.audio2loudness(a.numpy()) for a in audio]
+        return np.stack([SIL.loudness_to_raw_mask(l, q_levels, k_size) for l in loud]), (np.stack(loud) if want_loudness else None)
+    sil.sound_masks = sound_masks
+    return dict(W=W, SP=SP, om=om, stand=stand, tk=tk)
+
+
+def test_ragged_prompts_and_caps_match_oracle_window_by_window(env):
+    from stable_ts_b200.decode import DecodingOptions, decode_windows
+    W, SP, om, stand, tk = (env[k] for k in ("W", "SP", "om", "stand", "tk"))
+    audios = [SP.synth_audio(480000, seed=31 + i) for i in range(3)]
+    g = torch.Generator().manual_seed(5)
+    prompts = [[], torch.randint(300, 40000, (9,), generator=g).tolist(), torch.randint(300, 40000, (260,), generator=g).tolist()]
+    enc = stand.encode(stand.log_mel(torch.stack(audios)))
+    res, ex = decode_windows(stand, tk, enc, DecodingOptions(language="en", sample_len=12), prompts=prompts)
+    for b, (a, p) in enumerate(zip(audios, prompts)):
+        mel = W.pad_or_trim(W.log_mel_spectrogram(a, om.dims.n_mels), 3000)
+        ref, _, _ = SP.decode_window(om, mel, language="en", sample_len=12, prompt=p or None)
+        assert res[b].tokens == ref.tokens
+        assert abs(res[b].avg_logprob - ref.avg_logprob) < 1e-4 and abs(res[b].no_speech_prob - ref.no_speech_prob) < 1e-6
+    # n_ctx stop (decode.py:60): 1 + 223 + 1 = 225 initial tokens (tiny.en: sot_sequence is one token) leave room for 224 samples
+    # although sample_len is 230; the neighbour without a prompt runs the full script
+    forced = torch.randint(300, 40000, (230, 2), generator=g, dtype=torch.int32)
+    enc2 = stand.encode(stand.log_mel(torch.stack(audios[:2])))
+    res, ex = decode_windows(stand, tk, enc2, DecodingOptions(language="en", sample_len=230), prompts=[prompts[2], []],
+                             forced_tokens=forced)
+    assert ex["steps"] == 230 and len(res[0].tokens) == 224 and len(res[1].tokens) == 230
+    mel = W.pad_or_trim(W.log_mel_spectrogram(audios[0], om.dims.n_mels), 3000)
+    ref, _, rex = SP.decode_window(om, mel, language="en", sample_len=230, prompt=prompts[2], forced_tokens=forced[:, 0].tolist())
+    assert len(rex["step_argmax"]) == 224 and ex["step_argmax"][:224, 0].tolist() == rex["step_argmax"]
+    assert res[0].tokens == ref.tokens and abs(res[0].avg_logprob - ref.avg_logprob) < 1e-4
+
+
+class _InvCDF:
+    """Stand-in for torch.distributions.Categorical inside the oracle: first index whose running probability exceeds u."""
+    table_for_pass = None
+    pass_index = -1
+    step = 0
+
+    def __init__(self, logits):
+        self.logits = logits
+
+    def sample(self):
+        c = torch.softmax(self.logits.double(), -1).cumsum(-1)
+        u = _InvCDF.table_for_pass(_InvCDF.pass_index, c.shape[0])[_InvCDF.step]
+        _InvCDF.step += 1
+        return (c > u[:, None]).to(torch.uint8).argmax(-1)
+
+
+def _uniforms(pass_index, n_seq, rows=64):
+    g = torch.Generator().manual_seed(900 + pass_index)
+    return torch.rand(rows, n_seq, generator=g, dtype=torch.float64)
+
+
+@pytest.mark.parametrize("temps,carry", [((0.0, 0.4), True), ((0.0, 0.8), True), ((0.0, 0.4, 0.6), False)])
+def test_transcribe_fallback_prompt_and_seek_match_unmodified_reference(env, temps, carry):
+    import oracle.whisper_ref.decoding as odec
+    import stable_whisper.whisper_word_level.original_whisper as ow
+    SP, om, stand = env["SP"], env["om"], env["stand"]
+    audio = torch.cat([SP.synth_audio(480000, seed=21), SP.synth_audio(330000, seed=22)])
+    orig_cat, orig_dec = odec.Categorical, ow.decode_stable
+    _InvCDF.table_for_pass, _InvCDF.pass_index = _uniforms, -1
+
+    def counting_decode(model, seg, options, **kw):
+        if options.temperature > 0:
+            _InvCDF.pass_index += 1
+            _InvCDF.step = 0
+        return orig_dec(model, seg, options, **kw)
+    odec.Categorical, ow.decode_stable = _InvCDF, counting_decode
+    try:
+        theirs = ow.transcribe_stable(om, audio, language="en", temperature=temps, best_of=2, condition_on_previous_text=carry,
+                                      word_timestamps=True, vad=False, suppress_silence=False, suppress_ts_tokens=False,
+                                      regroup=False, verbose=None, fp16=False, ignore_compatibility=True, sample_len=16)
+    finally:
+        odec.Categorical, ow.decode_stable = orig_cat, orig_dec
+    n_ref_passes = _InvCDF.pass_index + 1
+    calls = []
+
+    def source(ti, steps, n_seq):
+        calls.append(ti)
+        return _uniforms(len(calls) - 1, n_seq)[:steps]
+    mine = stand.transcribe(audio, language="en", temperature=temps, best_of=2, condition_on_previous_text=carry, regroup=False,
+                            sample_len=16, shard_seconds=None, batch_windows=1, uniforms=source)
+    assert len(calls) == n_ref_passes and n_ref_passes >= 2
+    da, db = mine.to_dict(), theirs.to_dict()
+    assert len(da["segments"]) == len(db["segments"]) and len(da["segments"]) >= 2
+    for sa, sb in zip(da["segments"], db["segments"]):
+        assert sa["tokens"] == [int(t) for t in sb["tokens"]] and sa["seek"] == sb["seek"]
+        assert sa["temperature"] == sb["temperature"] and abs(sa["avg_logprob"] - sb["avg_logprob"]) < 1e-5
+        assert sa["start"] == sb["start"] and sa["end"] == sb["end"]
+        assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
+        for wa, wb in zip(sa["words"], sb["words"]):
+            assert wa["start"] == wb["start"] and wa["end"] == wb["end"]

@@ -161,7 +161,7 @@ def test_transcribe_method_returns_result_object():
     from oracle import stable_path as SP
     W, om, gm = _models("tiny.en", seed=3)
     audio = torch.cat([SP.synth_audio(480000, seed=21), SP.synth_audio(200000, seed=22)])
-    res = gm.transcribe(audio, language="en", regroup=False, sample_len=40)
+    res = gm.transcribe(audio, language="en", regroup=False, sample_len=40, temperature=0.0)
     d = res.to_dict()
     assert set(("text", "segments", "language")) <= set(d) and d["language"] == "en"
     # first window == the oracle's transcribe_window of the same samples (free-running greedy decode)
@@ -170,3 +170,78 @@ def test_transcribe_method_returns_result_object():
     mine = [s for s in d["segments"] if s["start"] < 30.0 and s["seek"] == 0.0]
     if ref:
         assert [s["tokens"] for s in mine[: len(ref)]] == [s["tokens"] for s in ref]
+
+
+class _InvCDF:
+    """Test-only stand-in for ``torch.distributions.Categorical`` inside the CPU oracle: the draw rule of ``stb_sample`` (first
+    index whose running probability exceeds u) fed from the same table of uniforms as the GPU path."""
+    table_for_pass = None        # callable(pass_index, n_seq) -> fp64 [rows, n_seq]
+    pass_index = -1
+    step = 0
+
+    def __init__(self, logits):
+        self.logits = logits
+
+    def sample(self):
+        c = torch.softmax(self.logits.double(), -1).cumsum(-1)
+        u = _InvCDF.table_for_pass(_InvCDF.pass_index, c.shape[0])[_InvCDF.step]
+        _InvCDF.step += 1
+        return (c > u[:, None]).to(torch.uint8).argmax(-1)
+
+
+def _extreme_uniforms(pass_index, n_seq, rows=64):
+    """u = 0 (first token with probability > 0) or 1 - 2^-24 (last one), alternating over sequences and passes: the drawn
+    token then depends on the logit FILTERS only, never on a near-tie of two running sums, so the CPU oracle and the GPU
+    draw the same tokens although their logits differ by ~1e-5 relative."""
+    hi = 1.0 - 2.0 ** -24
+    row = torch.tensor([0.0 if (s + pass_index) % 2 == 0 else hi for s in range(n_seq)], dtype=torch.float64)
+    return row.repeat(rows, 1)
+
+
+@pytest.mark.parametrize("temps,carry", [((0.0, 0.4), True), ((0.0, 0.8), True), ((0.0, 0.4), False)])
+def test_transcribe_fallback_and_prompt_carry_match_unmodified_reference(ref_env, temps, carry):
+    """Whole-audio ``transcribe`` (one sequential shard) == the UNMODIFIED transcribe_stable over the CPU oracle model:
+    temperature fallback with best_of draws (original_whisper.py:349-393), prompt carry-over and its reset after a window decoded
+    above temperature 0.5 (:533,696-698), data-dependent seek (:703-710)."""
+    import oracle.whisper_ref.decoding as odec
+    import stable_whisper.whisper_word_level.original_whisper as ow
+    from oracle import stable_path as SP
+    W, om, gm = _models("tiny.en", seed=3)
+    audio = torch.cat([SP.synth_audio(480000, seed=21), SP.synth_audio(330000, seed=22)])
+    # --- reference side
+    orig_cat, orig_dec = odec.Categorical, ow.decode_stable
+    _InvCDF.table_for_pass, _InvCDF.pass_index = _extreme_uniforms, -1
+
+    def counting_decode(model, seg, options, **kw):
+        if options.temperature > 0:
+            _InvCDF.pass_index += 1
+            _InvCDF.step = 0
+        return orig_dec(model, seg, options, **kw)
+    odec.Categorical, ow.decode_stable = _InvCDF, counting_decode
+    try:
+        theirs = ow.transcribe_stable(om, audio, language="en", temperature=temps, best_of=2, condition_on_previous_text=carry,
+                                      word_timestamps=True, vad=False, suppress_silence=False, suppress_ts_tokens=False,
+                                      regroup=False, verbose=None, fp16=False, ignore_compatibility=True, sample_len=24)
+    finally:
+        odec.Categorical, ow.decode_stable = orig_cat, orig_dec
+    n_ref_passes = _InvCDF.pass_index + 1
+    # --- B200 side: same uniforms, pass by pass
+    calls = []
+
+    def source(ti, steps, n_seq):
+        calls.append(ti)
+        return _extreme_uniforms(len(calls) - 1, n_seq, rows=steps).float()
+    mine = gm.transcribe(audio, language="en", temperature=temps, best_of=2, condition_on_previous_text=carry, regroup=False,
+                         sample_len=24, shard_seconds=None, batch_windows=1, uniforms=source)
+    assert len(calls) == n_ref_passes and n_ref_passes >= 1
+    da, db = mine.to_dict(), theirs.to_dict()
+    assert len(da["segments"]) == len(db["segments"])
+    for sa, sb in zip(da["segments"], db["segments"]):
+        assert sa["tokens"] == [int(t) for t in sb["tokens"]] and sa["seek"] == sb["seek"]
+        assert sa["temperature"] == sb["temperature"]
+        assert abs(sa["avg_logprob"] - sb["avg_logprob"]) < 1e-3
+        assert len(sa["words"]) == len(sb["words"])
+        for wa, wb in zip(sa["words"], sb["words"]):
+            assert wa["tokens"] == wb["tokens"]
+            assert abs(wa["start"] - wb["start"]) <= 0.0201 and abs(wa["end"] - wb["end"]) <= 0.0201
+    print(f"transcribe {temps} carry={carry}: {len(da['segments'])} segments, {n_ref_passes} sampled passes, identical to the reference")
