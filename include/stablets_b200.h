@@ -223,6 +223,10 @@ STB_API int stb_qk_postprocess_new(const float* qk, int B, int LH, int M, long l
                            int medfilt_width, int topk, float w_colnorm, float w_rownorm, float w_coverage, float* matrix,
                            long long ldm, void* ws, size_t ws_bytes, void* stream);
 
+/* y[i] = a * x[i] + b * y[i]: combines the head-averaged attention matrices of several models before the DTW
+ * (`extra_models`, stable_whisper/timing.py:177-189: the per-model weights are concatenated over heads and averaged). */
+STB_API int stb_axpby(float* y, const float* x, float a, float b, long long n, void* stream);
+
 /* a6 DTW + jump extraction (whisper.timing.dtw CPU semantics + stable_whisper/timing.py:195-198):
  *   x [B][R][ldx] fp32 (cost = -x when negate != 0), path over the R x F grid, strict-'<' tie rule, fp32 cost.
  *   jumps [B][R] int32 = first frame of every row on the path (clipped at 0).

@@ -92,6 +92,7 @@ _SIGS = {
     "stb_qkpost_new_ws_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "stb_qk_postprocess_new": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_int, c_int, c_float, c_int, c_int,
                                        c_float, c_float, c_float, c_void_p, c_longlong, c_void_p, c_size_t, c_void_p]),
+    "stb_axpby": (c_int, [c_void_p, c_void_p, c_float, c_float, c_longlong, c_void_p]),
     "stb_dtw_smem_bytes": (c_size_t, [c_int, c_int]),
     "stb_dtw_ws_bytes": (c_size_t, [c_int, c_int, c_int]),
     "stb_dtw": (c_int, [c_void_p, c_int, c_int, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

@@ -20,8 +20,7 @@ def get_b200_alignment_func(model: B200Whisper, tokenizer, options=None):
     """-> compute_timestamps(audio_segment fp32 [n<=480000], word_tokens) -> list of word dicts
     (same closure as stable_whisper/alignment.py:405-429: no gap padding, identity split, no punctuation merge)."""
     al = getattr(options, "align", None) if options is not None else None
-    if al is not None and getattr(al, "extra_models", None):
-        raise NotImplementedError("B200 path: extra_models is not implemented")
+    extra = getattr(al, "extra_models", None) if al is not None else None
     dyn = getattr(al, "dynamic_heads", None) if al is not None else None
     aligner = getattr(al, "aligner", "legacy") if al is not None else "legacy"
 
@@ -32,7 +31,7 @@ def get_b200_alignment_func(model: B200Whisper, tokenizer, options=None):
         add_word_timestamps_stable(segments=seg, model=model, tokenizer=tokenizer, audio=audio_segment,
                                    num_samples=int(audio_segment.size(-1)), split_callback=(lambda x, _: x),
                                    prepend_punctuations="", append_punctuations="", gap_padding=None, dynamic_heads=dyn,
-                                   aligner=aligner)
+                                   aligner=aligner, extra_models=extra)
         return [w for s in seg for w in s["words"]]
 
     return compute_timestamps

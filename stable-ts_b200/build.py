@@ -50,9 +50,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print("\n".join(logs))
     objs = [os.path.join(OBJ, s[:-3] + ".o") for s in sources()]
     if jobs or not os.path.exists(LIB):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-Xcompiler", "-fvisibility=hidden"], capture_output=True, text=True)
+        tmp = LIB + ".tmp"                                   # link aside, then rename: the library is replaced atomically
+        r = subprocess.run([NVCC, "-shared", "-o", tmp, *objs, "-Xcompiler", "-fvisibility=hidden"], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(tmp, LIB)
     return LIB
 
 

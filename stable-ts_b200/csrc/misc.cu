@@ -103,7 +103,22 @@ __global__ void split_f16_kernel(const float* __restrict__ src, long long rows, 
     }
 }
 
+// y = a * x + b * y
+__global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = a * x[i] + b * y[i];
+}
+
 }  // namespace stb
+
+extern "C" int stb_axpby(float* y, const float* x, float a, float b, long long n, void* stream) {
+    STB_REQUIRE(y && x && n >= 0, "stb_axpby: bad arguments");
+    if (n == 0) return STB_OK;
+    const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
+    stb::axpby_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, x, a, b, n);
+    STB_LAUNCH_OK();
+    return STB_OK;
+}
 
 extern "C" const char* stb_last_error(void) { return stb::get_error(); }
 extern "C" int stb_abi_version(void) { return 2; }

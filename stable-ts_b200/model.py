@@ -383,6 +383,16 @@ class B200Whisper(WhisperProtocol):
                                                  L.ptr(ws), ws.numel(), L.stream_ptr()))
         return out[:, :, :F]
 
+    @_on_device
+    def scale_add(self, y: torch.Tensor, x: torch.Tensor, a: float, b: float) -> torch.Tensor:
+        """y = a * x + b * y in place for two matrices returned by ``qk_postprocess*`` (same shape: the views' padded base
+        buffers are combined whole).  Used to average the attention matrices of ``extra_models`` (timing.py:177-189)."""
+        yb = y._base if y._base is not None else y
+        xb = x._base if x._base is not None else x
+        assert y.shape == x.shape and yb.shape == xb.shape and yb.is_contiguous() and xb.is_contiguous()
+        L.check(self._lib.stb_axpby(L.ptr(yb), L.ptr(xb.to(self.device)), float(a), float(b), yb.numel(), L.stream_ptr()))
+        return y
+
     # ---- a6 ----
     @_on_device
     def dtw(self, matrix: torch.Tensor, negate: bool = True, want_path: bool = False):

@@ -102,15 +102,29 @@ def _parse_dynamic_heads(dynamic_heads):
 
 def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfilt_width: int = 7, qk_scale: float = 1.0,
                   enc=None, ckv=None, dynamic_heads=None, aligner: Union[str, dict] = "legacy",
-                  return_intermediates: bool = False):
+                  return_intermediates: bool = False, extra_models: Optional[Sequence[B200Whisper]] = None):
     """Batched equivalent of ``_compute_jump_indices``: legacy alignment heads, per-token dynamic heads
     (``dynamic_heads``: True | count | "count,iterations") or the "new" aligner (``aligner="new"`` or a dict of its
     options), stable_whisper/timing.py:70-198.
+
+    ``extra_models`` (legacy / dynamic heads only, as in the reference, timing.py:177-189): every extra model runs its own
+    encoder + teacher-forced pass on the windows' audio; the per-model attention weights are averaged over ALL heads of all
+    models before the DTW (each model's head-mean weighted by its head count, combined on the device by stb_axpby) and the
+    token probabilities are averaged over the models.
 
     -> list (per window) of (jump_indices int array [N+1], text_token_probs list[N]) (+ intermediates).
     """
     count, iters = _parse_dynamic_heads(dynamic_heads)
     new = aligner != "legacy"
+    extra_models = list(extra_models or [])
+    if extra_models and not new:
+        bad = {type(m) for m in extra_models} - {type(model)}
+        if bad:
+            raise NotImplementedError(f"Got unsupported model type(s): {bad}")          # timing.py:219-220
+        if any(j.audio is None for j in jobs):
+            raise ValueError("extra_models: every window needs its audio (each model runs its own encoder)")
+    if new:
+        extra_models = []                                  # the "new" aligner ignores them (timing.py:174-175)
     if count is None and not new and getattr(model, "missing_alignment_heads", False):
         count = 6
     all_heads = bool(count) or new
@@ -119,6 +133,8 @@ def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfi
     fw = window_batch_forward(model, tokenizer, jobs, enc=enc, ckv=ckv, heads="all" if all_heads else None,
                               reuse_buffers=not return_intermediates)
     S, logits, qk, M = fw["S"], fw["logits"], fw["qk"], fw["M"]
+    if extra_models:
+        return _align_windows_multi(model, extra_models, tokenizer, jobs, fw, count, iters, medfilt_width, qk_scale)
     inter = []
     # windows with the same (N, F) share one post-processing / DTW launch
     groups = {}
@@ -130,8 +146,7 @@ def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfi
         qk_g = qk if len(idx) == len(jobs) else qk.index_select(0, sel).contiguous()
         if new:
             kw = dict(aligner) if isinstance(aligner, dict) else {}
-            if kw.pop("char_split", False):
-                raise NotImplementedError("B200 path: aligner={'char_split': True} is not implemented")
+            kw.pop("char_split", None)                     # only changes the token script (add_word_timestamps_stable)
             # the reference slices [S:-1] of the decoder rows it ran (M_i = S + N + 2); padded rows are excluded by
             # running the scoring on a view of exactly those rows
             Mi = S + N + 2
@@ -170,9 +185,64 @@ def align_windows(model: B200Whisper, tokenizer, jobs: List[WindowJob], *, medfi
     return results
 
 
-def word_timings_from_jumps(jumps: np.ndarray, token_probs: List[float], words, word_tokens) -> List[WordTiming]:
-    """stable_whisper/timing.py:251-253,289-306; ``word_tokens`` already ends with the [eot] pseudo-word."""
+def _align_windows_multi(model, extra_models, tokenizer, jobs, fw_main, count, iters, medfilt_width, qk_scale):
+    """``align_windows`` with ``extra_models`` (timing.py:177-189).  One (N, F) group at a time, every model's forward done
+    once; per dynamic-heads iteration the matrices of all models are combined and one DTW gives the shared jumps."""
+    models = [model] + list(extra_models)
+    fws = [fw_main] + [window_batch_forward(m, tokenizer, jobs, heads="all" if count else None, reuse_buffers=False)
+                       for m in extra_models]
+    S, M = fw_main["S"], fw_main["M"]
+    groups = {}
+    for i, j in enumerate(jobs):
+        groups.setdefault((len(j.text_tokens), n_frames_for(j.num_samples)), []).append(i)
+    results = [None] * len(jobs)
+    for (N, F), idx in groups.items():
+        tgt = torch.tensor([jobs[i].text_tokens for i in idx], dtype=torch.int32).reshape(-1)
+        probs = []
+        for m, fw in zip(models, fws):
+            rows = torch.cat([fw["logits"][i, S:S + N] for i in idx]) if N > 0 else fw["logits"][:0, 0]
+            p = m.token_probs(rows, tokenizer.eot, tgt)[0].cpu().numpy().astype(np.float64) if N > 0 else np.zeros(0)
+            probs.append(p.reshape(len(idx), N))
+        heads = [count if count else len(m.alignment_head_pairs) for m in models]
+        total = float(sum(heads))
+        jumps = None
+        # the reference replaces the main cache's probabilities by the mean over [extras..., main] on EVERY iteration
+        # (timing.py:183-189), so from the second iteration on the previous mean takes the main model's place
+        main_probs = probs[0]
+        for it in range(iters or 1):
+            combined = None
+            for m, fw, h in zip(models, fws, heads):
+                sel = torch.tensor(idx, device=m.device)
+                qk_g = fw["qk"] if len(idx) == len(jobs) else fw["qk"].index_select(0, sel).contiguous()
+                if count:
+                    # only the MAIN model's cache ever receives jump_indices (timing.py:198): the extra models pick their
+                    # heads from the attention peaks on every iteration
+                    mat = m.qk_postprocess_dynamic(qk_g, S, F, R=N + 1, count=count, prev_jumps=jumps if m is model else None,
+                                                   reuse_softmax=it > 0, qk_scale=qk_scale, medfilt_width=medfilt_width)
+                else:
+                    mat = m.qk_postprocess(qk_g, S, F, R=N + 1, qk_scale=qk_scale, medfilt_width=medfilt_width)
+                if combined is None:
+                    combined = model.scale_add(mat, mat, h / total, 0.0)
+                else:
+                    model.scale_add(combined, mat, h / total, 1.0)
+            jumps = model.dtw(combined, negate=True)
+            main_probs = np.mean(np.stack(probs[1:] + [main_probs]), axis=0)
+        jumps_h = jumps.cpu().numpy()
+        for k, i in enumerate(idx):
+            results[i] = (jumps_h[k].astype(np.int64), main_probs[k].tolist())
+    return results
+
+
+def word_timings_from_jumps(jumps: np.ndarray, token_probs: List[float], words, word_tokens, ignore_tokens=None,
+                            word_tokens_out=None) -> List[WordTiming]:
+    """stable_whisper/timing.py:251-253,289-306; ``word_tokens`` already ends with the [eot] pseudo-word.
+    ``ignore_tokens`` / ``word_tokens_out``: the char_split form (timing.py:240-253,299-301): boundaries are counted in the
+    character tokens, a word that starts with the space token starts one token later, and the returned WordTiming carries
+    the word's ORIGINAL tokens."""
     wb = np.pad(np.cumsum([len(t) for t in word_tokens[:-1]]), (1, 0))
+    if ignore_tokens:
+        itk = list(ignore_tokens)
+        wb = wb + np.array([list(t[:len(itk)]) == itk for t in word_tokens], dtype=wb.dtype)
     jump_times = jumps / TOKENS_PER_SECOND
     # plain Python floats from here on: same float64 values as the reference's numpy scalars, without ~3 us of numpy
     # scalar overhead per word and per round() on the host path (120 windows x ~170 words per step)
@@ -180,6 +250,9 @@ def word_timings_from_jumps(jumps: np.ndarray, token_probs: List[float], words, 
     bounds = wb.tolist()
     tp = token_probs if isinstance(token_probs, list) else list(token_probs)
     probs = [(math.fsum(tp[i:j]) / (j - i)) if j > i else float("nan") for i, j in zip(bounds[:-1], bounds[1:])]
+    if word_tokens_out is not None:
+        assert len(word_tokens_out) == len(word_tokens)
+        word_tokens = word_tokens_out
     return [WordTiming(w, t, s, e, p) for w, t, s, e, p in zip(words, word_tokens, starts, ends, probs)]
 
 
@@ -187,19 +260,25 @@ def find_alignment_stable(model: B200Whisper, tokenizer, text_tokens: List[int],
                           num_samples: int, *, medfilt_width: int = 7, qk_scale: float = 1.0, token_split=None,
                           enc=None, dynamic_heads=None, aligner: Union[str, dict] = "legacy", extra_models=None,
                           ts_num: int = 0, ts_noise=None) -> List[WordTiming]:
-    """One window (stable_whisper/timing.py:202-306).  ``audio`` replaces ``mel`` (the log-mel runs on the device)."""
-    if extra_models:
-        raise NotImplementedError("extra_models is not supported by the B200 path yet")
+    """One window (stable_whisper/timing.py:202-306).  ``audio`` replaces ``mel`` (the log-mel runs on the device).
+    ``token_split`` = (words, word_tokens) or, for the "new" aligner's char_split, (words, dict(tokens, tokens_orig,
+    ignore_tokens)) as ``split_word_tokens`` returns it (timing.py:240-246)."""
+    assert isinstance(aligner, dict) or aligner in ("new", "legacy"), f'aligner must be "new"/"legacy", got "{aligner}"'
+    orig = itk = None
     if token_split is None:
         words, word_tokens = tokenizer.split_to_word_tokens(list(text_tokens) + [tokenizer.eot])
     else:
         words, word_tokens = token_split
+        if isinstance(word_tokens, dict):
+            orig = list(word_tokens["tokens_orig"]) + [[tokenizer.eot]]
+            itk = word_tokens["ignore_tokens"]
+            word_tokens = word_tokens["tokens"]
         words = list(words) + [tokenizer.decode([tokenizer.eot])]
         word_tokens = list(word_tokens) + [[tokenizer.eot]]
     job = WindowJob(list(text_tokens), num_samples, audio)
     (jumps, probs), = align_windows(model, tokenizer, [job], medfilt_width=medfilt_width, qk_scale=qk_scale, enc=enc,
-                                    dynamic_heads=dynamic_heads, aligner=aligner)
-    return word_timings_from_jumps(jumps, probs, words, word_tokens)
+                                    dynamic_heads=dynamic_heads, aligner=aligner, extra_models=extra_models)
+    return word_timings_from_jumps(jumps, probs, words, word_tokens, ignore_tokens=itk, word_tokens_out=orig)
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -239,11 +318,13 @@ def _split_tokens(tokens: List[int], tokenizer):
 
 
 def split_word_tokens(segments: List[dict], tokenizer, *, padding: Union[str, int, None] = None,
-                      split_callback: Optional[Callable] = None, pad_first_seg: bool = True):
-    """stable_whisper/timing.py:344-392 (char_split is part of the 'new' aligner and not mirrored)."""
+                      split_callback: Optional[Callable] = None, pad_first_seg: bool = True, char_split: bool = False):
+    """stable_whisper/timing.py:344-392.  char_split (the "new" aligner's character-level script): the token script is the
+    encoding of every character of every word; ``word_tokens`` becomes dict(tokens=per-word character tokens,
+    tokens_orig=the words' own tokens, ignore_tokens=encode(' '))."""
     if padding is not None:
         padding = tokenizer.encode(padding) if isinstance(padding, str) else [padding]
-    tokens, seg_indices, words, word_tokens = [], [], [], []
+    tokens, seg_indices, words, word_tokens, word_char_tokens = [], [], [], [], []
     for i, seg in enumerate(segments):
         text_toks = [t for t in seg["tokens"] if not isinstance(t, int) or t < tokenizer.eot]
         cw, cwt = _split_tokens(text_toks, tokenizer) if split_callback is None else split_callback(text_toks, tokenizer)
@@ -254,9 +335,16 @@ def split_word_tokens(segments: List[dict], tokenizer, *, padding: Union[str, in
             words.append(None)
             word_tokens.append(padding)
         seg_indices.extend([i] * len(cw))
-        tokens.extend(chain.from_iterable(cwt))
+        if char_split:
+            cct = [[ct for ch in word for ct in tokenizer.encode(ch)] for word in cw]
+            word_char_tokens.extend(cct)
+            tokens.extend(chain.from_iterable(cct))
+        else:
+            tokens.extend(chain.from_iterable(cwt))
         words.extend(cw)
         word_tokens.extend(cwt)
+    if char_split:
+        word_tokens = dict(tokens=word_char_tokens, tokens_orig=word_tokens, ignore_tokens=tokenizer.encode(" "))
     return tokens, (words, word_tokens), seg_indices
 
 
@@ -391,9 +479,17 @@ def add_word_timestamps_stable(*, segments: List[dict], model: B200Whisper, toke
         enc = model._encoding_of(audio_features)
     if enc is None and audio is None and mel is not None:
         enc = model.encode(mel.to(model.device, torch.float32))
-    text_tokens, words, word_tokens, seg_indices = _prepare_word_timestamps(segments, tokenizer, split_callback, gap_padding,
-                                                                            pad_first_seg)
-    alignment = find_alignment_stable(model, tokenizer, text_tokens, audio, num_samples, token_split=(words[:-1], word_tokens[:-1]),
+    # timing.py:442-444: char_split belongs to the "new" aligner's options and switches the gap padding off
+    # (the key is popped from the CALLER's dict, exactly as the reference does: with one options object shared by all windows
+    # of an align() call only the first window is character-split there, and therefore here)
+    char_split = bool(isinstance(aligner, dict) and aligner.pop("char_split", False))
+    if char_split:
+        gap_padding = None
+    for seg in segments:
+        seg["words"] = []
+    text_tokens, token_split, seg_indices = split_word_tokens(segments, tokenizer, padding=gap_padding, split_callback=split_callback,
+                                                              pad_first_seg=pad_first_seg, char_split=char_split)
+    alignment = find_alignment_stable(model, tokenizer, text_tokens, audio, num_samples, token_split=token_split,
                                       enc=enc, aligner=aligner, **kwargs)
     _finish_word_timestamps(segments, alignment, seg_indices, prepend_punctuations, append_punctuations, min_word_dur,
                             gap_padding, pad_first_seg)

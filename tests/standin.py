@@ -192,3 +192,42 @@ class OracleStepEngine:
             self.next[b] = nxt
             self.seq[b, 4] = int(nxt == tk.eot)
         self.seq[:, 5] = torch.tensor(self.sum_lp, dtype=torch.float32).view(torch.int32)
+
+
+def _qk_postprocess_new(self, qk_all, S, F, R=None, topk=20, w_colnorm=1.0, w_rownorm=1.0, w_coverage=0.0, qk_scale=1.0,
+                        medfilt_width=7):
+    """The "new" aligner's matrix (stable_whisper/timing.py:115-163) from the all-head QK block, via the oracle."""
+    B, LH, M, _ = qk_all.shape
+    Lh, H = self.dims.n_text_layer, self.dims.n_text_head
+    out = []
+    for b in range(B):
+        qks = [qk_all[b, l * H:(l + 1) * H, :, :1500][None] for l in range(Lh)]
+        out.append(SP.attention_matrix_new(qks, S, F * 320, medfilt_width, qk_scale, topk=topk, w_colnorm=w_colnorm,
+                                           w_rownorm=w_rownorm, w_coverage=w_coverage))
+    return torch.stack(out)
+
+
+def _scale_add(self, y, x, a, b):
+    y.mul_(b).add_(x * a) if b != 0.0 else y.copy_(x * a)
+    return y
+
+
+OracleBackedModel.qk_postprocess_new = _qk_postprocess_new
+OracleBackedModel.scale_add = _scale_add
+
+
+def _qk_postprocess_dynamic(self, qk_all, S, F, R=None, count=6, prev_jumps=None, reuse_softmax=False, qk_scale=1.0,
+                            medfilt_width=7):
+    """Per-token dynamic heads (stable_whisper/timing.py:85-103) from the all-head QK block, via the oracle -> head mean."""
+    B, LH, M, _ = qk_all.shape
+    Lh, H = self.dims.n_text_layer, self.dims.n_text_head
+    R = M - 1 - S if R is None else R
+    out = []
+    for b in range(B):
+        qks = [qk_all[b, l * H:(l + 1) * H, :S + R + 1, :1500][None] for l in range(Lh)]
+        pj = None if prev_jumps is None else prev_jumps[b].cpu().numpy()
+        out.append(SP.attention_weights_dynamic(qks, S, F * 320, count, pj, medfilt_width, qk_scale).mean(dim=0))
+    return torch.stack(out)
+
+
+OracleBackedModel.qk_postprocess_dynamic = _qk_postprocess_dynamic

@@ -245,3 +245,42 @@ def test_transcribe_fallback_and_prompt_carry_match_unmodified_reference(ref_env
             assert wa["tokens"] == wb["tokens"]
             assert abs(wa["start"] - wb["start"]) <= 0.0201 and abs(wa["end"] - wb["end"]) <= 0.0201
     print(f"transcribe {temps} carry={carry}: {len(da['segments'])} segments, {n_ref_passes} sampled passes, identical to the reference")
+
+
+@pytest.mark.parametrize("variant", ["char_split", "extra_models", "extra_models_dynamic"])
+def test_timing_variants_match_unmodified_reference(ref_env, variant):
+    """``extra_models`` and the "new" aligner's ``char_split`` (timing.py:177-189,240-253,380-390,442-444) through
+    ``add_word_timestamps_stable`` on the kernels vs the unmodified function over the CPU oracle models."""
+    import oracle.whisper_ref as W
+    import stable_whisper.timing as ref_timing
+    from oracle import stable_path as SP
+    from stable_ts_b200.model import from_oracle
+    from stable_ts_b200.timing import add_word_timestamps_stable
+    from stable_ts_b200.tokenizer import get_tokenizer
+    om, om2 = W.build_model("tiny", seed=5), W.build_model("tiny", seed=6)
+    gm, gm2 = from_oracle(om), from_oracle(om2)
+    otk = W.tokenizer.get_tokenizer(True, num_languages=om.num_languages, language="en", task="transcribe")
+    tk = get_tokenizer(gm, language="en", task="transcribe", synthetic=True)
+    audio = SP.synth_audio(400000, seed=51)
+    mel = W.pad_or_trim(W.log_mel_spectrogram(audio, om.dims.n_mels, padding=80000), 3000)
+    script = SP.synth_token_script(36, otk.eot, seed=52)
+    theirs = [dict(seek=0.0, tokens=script[:20]), dict(seek=0.0, tokens=script[20:])]
+    mine = copy.deepcopy(theirs)
+    kw_ref, kw = {}, {}
+    if variant == "char_split":
+        kw_ref, kw = dict(aligner={"char_split": True}), dict(aligner={"char_split": True})
+    else:
+        dyn = "4,2" if variant.endswith("dynamic") else None
+        kw_ref, kw = dict(extra_models=[om2], dynamic_heads=dyn), dict(extra_models=[gm2], dynamic_heads=dyn)
+    ref_timing.add_word_timestamps_stable(segments=theirs, model=om, tokenizer=otk, mel=mel, num_samples=400000, **kw_ref)
+    add_word_timestamps_stable(segments=mine, model=gm, tokenizer=tk, audio=audio, num_samples=400000, **kw)
+    n, worst = 0, 0.0
+    for a, b in zip(mine, theirs):
+        assert len(a["words"]) == len(b["words"]) and len(a["words"]) > 0
+        for wa, wb in zip(a["words"], b["words"]):
+            assert wa["word"] == wb["word"] and list(wa["tokens"]) == list(wb["tokens"])
+            worst = max(worst, abs(wa["start"] - wb["start"]), abs(wa["end"] - wb["end"]))
+            assert abs(wa["probability"] - wb["probability"]) <= 2e-3 * abs(wb["probability"])
+            n += 1
+    print(f"{variant}: {n} words, worst |dt| {worst * 1e3:.0f} ms vs the unmodified reference")
+    assert worst <= 0.0201
