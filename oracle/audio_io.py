@@ -14,6 +14,8 @@ ZEROS, ROLLOFF, BETA = 24, 0.94, 10.0
 
 
 def polyphase_table(L: int, M: int) -> np.ndarray:
+    if L == M:                                                   # same rate: identity (the reference's ffmpeg would not resample)
+        return np.ones((1, 1), dtype=np.float64)
     scale = min(1.0, L / M)
     fc = 0.5 * ROLLOFF * scale
     half_width = ZEROS / scale

@@ -74,6 +74,8 @@ def resample_ratio(in_rate: int, out_rate: int = SAMPLE_RATE) -> Tuple[int, int]
 def polyphase_table(L_up: int, M_down: int, zeros: int = ZEROS, rolloff: float = ROLLOFF, beta: float = BETA) -> np.ndarray:
     """[L][taps] fp32: tab[p][j] = h((j - taps//2) - p / L) in INPUT samples, h = windowed sinc with cutoff
     rolloff * min(1, L/M) / 2 cycles per input sample; each branch scaled to unit DC gain."""
+    if L_up == M_down:                                           # same rate: no filter at all (ffmpeg inserts no resampler either)
+        return np.ones((1, 1), dtype=np.float32)
     scale = min(1.0, L_up / M_down)
     fc = 0.5 * rolloff * scale                                   # cycles / input sample
     half_width = zeros / scale                                   # support in input samples (per side)

@@ -76,7 +76,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 bool pdl_enabled();   // STB_PDL=0 disables (misc.cu)
 // run-time switches (stb_set_option / stb_get_option, misc.cu); defaults come from the environment variable of the same
 // meaning so a whole process can be flipped without code (STB_DECODE_SPLITK_LEGACY)
-enum Option { OPT_DECODE_SPLITK_LEGACY = 0, OPT_XATTN_PERSIST, OPT_COUNT };
+enum Option { OPT_DECODE_SPLITK_LEGACY = 0, OPT_COUNT };
 int option(Option o);
 
 template <typename... KArgs, typename... Args>

@@ -294,150 +294,6 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
     }
 }
 
-// PERSISTENT variant (option "xattn_persist"): 2 CTAs per SM, each walks the work items (b, h, split) round-robin with a
-// double-buffered shared-memory tile, so the bulk copies of item i+1 are in flight while item i is reduced, merged and its
-// partial written -- no CTA launch/drain bubble per 48 KB of input.  Same arithmetic, same partial/ticket protocol.
-__global__ void __launch_bounds__(128, 2)
-decode_cross_attn_persist_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const __half* __restrict__ v_hi, int d,
-                                 int T, int H, int n_items, float* __restrict__ partial, int* __restrict__ tickets,
-                                 __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32) {
-    extern __shared__ __align__(128) uint8_t x_smem[];       // 2 buffers x [K rows | V rows][XS_KEYS][128 B]
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ float s_m[4][4], s_l[4][4];
-    __shared__ float s_acc[4][4][64];
-    __shared__ int s_last;
-    constexpr uint32_t BUF = 2 * XS_KEYS * 128;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sub = lane & 7, grp = lane >> 3, g16 = w * 4 + grp;
-    if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    auto issue = [&](int item, int buf) {                    // thread 0 only
-        const int split = item % XS, bh = item / XS;
-        const int key0 = split * XS_KEYS, n = max(min(T, key0 + XS_KEYS) - key0, 0);
-        if (n <= 0) return;
-        const long long row0 = (long long)bh * T + key0;
-        const uint32_t bytes = (uint32_t)n * 128u;
-        uint8_t* dst = x_smem + (size_t)buf * BUF;
-        mbar_arrive_expect_tx(&s_bar[buf], 2 * bytes);
-        bulk_load_1d(dst, k_hi + row0 * 64, bytes, &s_bar[buf]);
-        bulk_load_1d(dst + XS_KEYS * 128, v_hi + row0 * 64, bytes, &s_bar[buf]);
-    };
-    const int first = blockIdx.x, stride = gridDim.x;
-    if (threadIdx.x == 0 && first < n_items) issue(first, 0);
-    pdl_trigger();
-    pdl_wait();                                              // q comes from the preceding linear
-    int it = 0;
-    for (int item = first; item < n_items; item += stride, ++it) {
-        const int buf = it & 1;
-        if (threadIdx.x == 0 && item + stride < n_items) issue(item + stride, buf ^ 1);
-        const int split = item % XS, bh = item / XS, h = bh % H, b = bh / H;
-        const int key0 = split * XS_KEYS, n = max(min(T, key0 + XS_KEYS) - key0, 0);
-        float qr[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e] * 0.125f;
-        float m = -INFINITY, l = 0.f, acc[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-        if (n > 0) {
-            mbar_wait(&s_bar[buf], (uint32_t)((it >> 1) & 1), 50 + buf);
-            const uint8_t* kc = x_smem + (size_t)buf * BUF + sub * 16;
-            const uint8_t* vc = kc + XS_KEYS * 128;
-            for (int j0 = g16; j0 < n; j0 += 64) {
-                float sc[4];
-                uint4 vh[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = j0 + u * 16;
-                    const bool ok = j < n;
-                    const uint4 kh = ok ? *reinterpret_cast<const uint4*>(kc + j * 128) : make_uint4(0, 0, 0, 0);
-                    vh[u] = ok ? *reinterpret_cast<const uint4*>(vc + j * 128) : make_uint4(0, 0, 0, 0);
-                    float kf[8];
-                    unpack8(kh, kf);
-                    float s = 0.f;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) s = fmaf(qr[e], kf[e], s);
-                    s += __shfl_xor_sync(0xffffffffu, s, 1);
-                    s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    s += __shfl_xor_sync(0xffffffffu, s, 4);
-                    sc[u] = ok ? s : -INFINITY;
-                }
-                const float mn = fmaxf(fmaxf(m, sc[0]), fmaxf(fmaxf(sc[1], sc[2]), sc[3]));
-                const float corr = expf(m - mn);
-                l *= corr;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[e] *= corr;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float p = expf(sc[u] - mn);
-                    float vf[8];
-                    unpack8(vh[u], vf);
-                    l += p;
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e]);
-                }
-                m = mn;
-            }
-        }
-        if (sub == 0) { s_m[w][grp] = m; s_l[w][grp] = l; }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s_acc[w][grp][sub * 8 + e] = acc[e];
-        __syncthreads();                                     // also: every thread is done reading this buffer
-        float* part = partial + ((long long)bh * XS + split) * 66;
-        if (threadIdx.x < 64) {
-            float M = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) M = fmaxf(M, s_m[i >> 2][i & 3]);
-            float Lsum = 0.f, o = 0.f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float mi = s_m[i >> 2][i & 3];
-                const float sc = (mi == -INFINITY) ? 0.f : expf(mi - M);
-                Lsum += s_l[i >> 2][i & 3] * sc;
-                o += s_acc[i >> 2][i & 3][threadIdx.x] * sc;
-            }
-            part[2 + threadIdx.x] = o;
-            if (threadIdx.x == 0) { part[0] = M; part[1] = Lsum; }
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int t = atomicAdd(tickets + bh, 1);
-            s_last = (t == XS - 1);
-            if (s_last) tickets[bh] = 0;
-        }
-        __syncthreads();
-        if (s_last && threadIdx.x < 64) {
-            __threadfence();
-            const float* p0 = partial + (long long)bh * XS * 66;
-            float M = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < XS; ++i) M = fmaxf(M, __ldcg(p0 + i * 66));
-            float Lsum = 0.f, o = 0.f;
-#pragma unroll
-            for (int i = 0; i < XS; ++i) {
-                const float mi = __ldcg(p0 + i * 66);
-                const float sc = (mi == -INFINITY) ? 0.f : expf(mi - M);
-                Lsum += __ldcg(p0 + i * 66 + 1) * sc;
-                o += __ldcg(p0 + i * 66 + 2 + threadIdx.x) * sc;
-            }
-            o /= Lsum;
-            const long long oo = (long long)b * d + h * 64 + threadIdx.x;
-            if (out_f32) out_f32[oo] = o;
-            if (out_hi) {
-                __half hi, lo;
-                split_f16(o, hi, lo);
-                out_hi[oo] = hi;
-                if (out_lo) out_lo[oo] = lo;
-            }
-        }
-        __syncthreads();                                     // s_m / s_acc / s_last are reused by the next item
-    }
-}
-
 // V^T plane [B][H][64][Tp] fp16 -> V head-major [B][H][T][64] (decode-step layout).  64 x 64 smem tile transpose.
 __global__ void __launch_bounds__(256) v_headmajor_kernel(const __half* __restrict__ vT_hi, int T, int Tp,
                                                           __half* __restrict__ v_hi) {
@@ -709,21 +565,6 @@ int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int
         STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM));
         STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[dev] = true;
-    }
-    if (option(OPT_XATTN_PERSIST) != 0) {
-        static bool attr_p[64] = {};
-        constexpr int PSMEM = 2 * 2 * XS_KEYS * 128;
-        if (dev >= 0 && dev < 64 && !attr_p[dev]) {
-            STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PSMEM));
-            STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            attr_p[dev] = true;
-        }
-        const int n_items = B * H * XS;
-        const int grid = min(n_items, 2 * sm_count());
-        STB_CUDA_OK(launch_pdl(decode_cross_attn_persist_kernel, dim3(grid), dim3(128), (size_t)PSMEM, st, q, kv.k_hi, kv.v_hi, d,
-                               (int)STB_N_AUDIO_CTX, H, n_items, partial, tickets, oh, ol, of));
-        STB_LAUNCH_OK();
-        return STB_OK;
     }
     STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel, dim3(XS, H, B), dim3(128), (size_t)X_SMEM, st, q, kv.k_hi, kv.v_hi, d,
                            (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));

@@ -49,14 +49,22 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// exit barrier: nothing is published, the peers only need to know that this CTA has finished READING their tiles
+__device__ __forceinline__ void cluster_sync_relaxed() {
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t dsmem_addr(uint32_t local_addr, uint32_t rank) {
     uint32_t r;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ float dsmem_ld(uint32_t addr) {
-    float v;
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+// 16-byte load from a peer CTA's shared memory (volatile + memory clobber keep it behind the cluster barrier; the loads of
+// one reduction step go to distinct registers, so they still issue back to back and their latencies overlap)
+__device__ __forceinline__ float4 dsmem_ld4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
     return v;
 }
 
@@ -218,34 +226,76 @@ decode_linear_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_cons
     __syncwarp();
     cluster_sync_all();                                         // every peer's tile is complete and visible
     if (warp >= 2) {
-        const int q = warp & 3;
-        const int t = q * 32 + lane;
-        const int m = m0 + t;
+        // Reduce-scatter over distributed shared memory: rank r owns sequences [r BN / split, (r + 1) BN / split).  A thread
+        // handles 4 consecutive features of one sequence: it issues the 16-byte loads of ALL peers first (independent, so their
+        // DSMEM latencies overlap), adds them in rank order (bit-reproducible), applies the epilogue and stores 16 bytes.
+        const int e = (warp - 2) * 32 + lane;                  // 0 .. 127
+        const int quad = e & 31;                               // features m0 + 4 quad .. + 3
+        const int m = m0 + quad * 4;
         const int c0 = rank * BN / split, c1 = (rank + 1) * BN / split;
         const uint32_t local = smem_u32(tiles);
+        uint32_t peer[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) peer[p] = p < split ? dsmem_addr(local, (uint32_t)p) : 0u;
         pdl_wait();                                             // the residual is an earlier kernel's output
+        const bool vec = m + 3 < g.n && (g.ld_out & 3) == 0 && (g.res == nullptr || (g.ld_res & 3) == 0);
+        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g.bias != nullptr) {
+            if (m + 3 < g.n) bias = __ldg(reinterpret_cast<const float4*>(g.bias + m));
+            else {
+                if (m < g.n) bias.x = __ldg(g.bias + m);
+                if (m + 1 < g.n) bias.y = __ldg(g.bias + m + 1);
+                if (m + 2 < g.n) bias.z = __ldg(g.bias + m + 2);
+            }
+        }
         if (m < g.n) {
-            const float bias = g.bias != nullptr ? __ldg(g.bias + m) : 0.f;
-            for (int c = c0; c < c1 && c < g.B; ++c) {
-                float v = 0.f;
-                const uint32_t a = local + (uint32_t)((c * 128 + t) * 4);
-                for (int p = 0; p < split; ++p) v += dsmem_ld(dsmem_addr(a, (uint32_t)p));
-                v += bias;
-                if (g.act == STB_ACT_GELU) v = gelu_erf(v);
-                if (g.res != nullptr) v += g.res[(long long)c * g.ld_res + m];
-                const long long off = (long long)c * g.ld_out + m;
-                if (g.out_f32 != nullptr) g.out_f32[off] = v;
-                if (g.out_hi != nullptr) {
-                    __half hi, lo;
-                    split_f16(v, hi, lo);
-                    g.out_hi[off] = hi;
-                    if (g.out_lo != nullptr) g.out_lo[off] = lo;
+            for (int c = c0 + (e >> 5); c < c1 && c < g.B; c += 4) {
+                const uint32_t off = (uint32_t)((c * 128 + quad * 4) * 4);
+                float4 v[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p)
+                    if (p < split) v[p] = dsmem_ld4(peer[p] + off);
+                float4 a = v[0];
+#pragma unroll
+                for (int p = 1; p < 8; ++p)
+                    if (p < split) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+                a.x += bias.x; a.y += bias.y; a.z += bias.z; a.w += bias.w;
+                if (g.act == STB_ACT_GELU) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+                const long long off_o = (long long)c * g.ld_out + m;
+                if (vec) {
+                    if (g.res != nullptr) {
+                        const float4 r = *reinterpret_cast<const float4*>(g.res + (long long)c * g.ld_res + m);
+                        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
+                    }
+                    if (g.out_f32 != nullptr) *reinterpret_cast<float4*>(g.out_f32 + off_o) = a;
+                    if (g.out_hi != nullptr) {
+                        __half h[4], l[4];
+                        split_f16(a.x, h[0], l[0]); split_f16(a.y, h[1], l[1]);
+                        split_f16(a.z, h[2], l[2]); split_f16(a.w, h[3], l[3]);
+                        *reinterpret_cast<uint2*>(g.out_hi + off_o) = *reinterpret_cast<const uint2*>(h);
+                        if (g.out_lo != nullptr) *reinterpret_cast<uint2*>(g.out_lo + off_o) = *reinterpret_cast<const uint2*>(l);
+                    }
+                } else {
+                    const float vals[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (m + j >= g.n) break;
+                        float x = vals[j];
+                        if (g.res != nullptr) x += g.res[(long long)c * g.ld_res + m + j];
+                        if (g.out_f32 != nullptr) g.out_f32[off_o + j] = x;
+                        if (g.out_hi != nullptr) {
+                            __half hi, lo;
+                            split_f16(x, hi, lo);
+                            g.out_hi[off_o + j] = hi;
+                            if (g.out_lo != nullptr) g.out_lo[off_o + j] = lo;
+                        }
+                    }
                 }
             }
         }
     }
     __syncwarp();
-    cluster_sync_all();                                         // nobody exits while a peer may still read its tile
+    cluster_sync_relaxed();                                     // nobody exits while a peer may still read its tile
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -254,13 +304,14 @@ decode_linear_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_cons
     }
 }
 
-// largest cluster size in {8, 4, 2, 1} such that every rank gets at least one k block and all clusters are co-resident
-// with margin for GPC granularity (clusters are placed inside one GPC)
+// cluster size in 1..8 (every size up to 8 is portable) that puts the most CTAs on the machine: every rank gets at least
+// one k block, and all clusters are co-resident with margin for GPC granularity (a cluster lives inside one GPC: with
+// 16 / 18 / 20 SMs per GPC, 128 CTAs fit for every cluster size)
 int decode_linear_split(int n, int k) {
     const int mt = cdiv(n, 128), nkb = k / 64;
     const int budget = sm_count() >= 140 ? 128 : (sm_count() * 7) / 8;
     int split = 1;
-    for (int s = 2; s <= 8; s *= 2)
+    for (int s = 2; s <= 8; ++s)
         if (s <= nkb && (long long)mt * s <= budget) split = s;
     return split;
 }

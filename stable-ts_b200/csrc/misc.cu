@@ -60,8 +60,6 @@ static const OptDef g_opt_defs[OPT_COUNT] = {
     // 1: decode-step linears as round 1 ran them (swapped split-K GEMM with partials in L2 + finish kernel) instead of the
     // cluster kernel of decode_linear.cu -- kept for A/B timing of the two paths on the same box
     {"decode_splitk_legacy", "STB_DECODE_SPLITK_LEGACY", 0},
-    // 1: decode cross-attention as a persistent, double-buffered kernel (2 CTAs per SM) instead of one CTA per (b, h, split)
-    {"xattn_persist", "STB_XATTN_PERSIST", 0},
 };
 static int g_opt[OPT_COUNT];
 static bool g_opt_init = false;

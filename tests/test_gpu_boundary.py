@@ -168,8 +168,8 @@ def test_transcribe_method_returns_result_object():
     otk = W.tokenizer.get_tokenizer(False)
     ref, _ = SP.transcribe_window(om, otk, audio[:480000], language="en", sample_len=40, max_instant_words=0.5)
     mine = [s for s in d["segments"] if s["start"] < 30.0 and s["seek"] == 0.0]
-    if ref:
-        assert [s["tokens"] for s in mine[: len(ref)]] == [s["tokens"] for s in ref]
+    if ref:     # (WhisperResult.to_dict lists a segment's TEXT tokens -- its words' tokens -- without the timestamp tokens)
+        assert [s["tokens"] for s in mine[: len(ref)]] == [[t for t in s["tokens"] if t < otk.eot] for s in ref]
 
 
 class _InvCDF:
