@@ -273,11 +273,14 @@ STB_API int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int32
  *    position (positional embedding row) is pos - seq_off[b], and its self-attention reads cache rows [seq_off[b], pos] only, so
  *    every sequence samples its first token at the same step.  Steps with pos < seq_off[b] are idle for b (any token id).
  *    cache_rows: rows per sequence of the K/V caches, n_text_ctx <= cache_rows <= 2 n_text_ctx (stb_decode_state_bytes_rows).
- *    seq_off == NULL and cache_rows == n_text_ctx is stb_decode_step. */
+ *    kv_total / kv_off: `cross_kv` was built by stb_cross_kv for kv_total windows and the B sequences of this call are its
+ *    windows [kv_off, kv_off + B): two halves of a batch can be stepped concurrently on two streams over one block (their
+ *    latency-bound linear layers then overlap the other half's HBM-bound cross-attention).  kv_total <= 0 means (B, 0).
+ *    seq_off == NULL, cache_rows == n_text_ctx and kv_total == B is stb_decode_step. */
 STB_API size_t stb_decode_state_bytes_rows(const stb_model* m, int B, int cache_rows);
 STB_API int stb_decode_step_ragged(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const int32_t* seq_off,
-                           int cache_rows, const void* cross_kv, void* state, float* logits_out, long long ld_logits, void* ws,
-                           size_t ws_bytes, void* stream);
+                           int cache_rows, const void* cross_kv, int kv_total, int kv_off, void* state, float* logits_out,
+                           long long ld_logits, void* ws, size_t ws_bytes, void* stream);
 
 /* per-sequence sampling state kept on the device */
 typedef struct {

@@ -76,8 +76,12 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 bool pdl_enabled();   // STB_PDL=0 disables (misc.cu)
 // run-time switches (stb_set_option / stb_get_option, misc.cu); defaults come from the environment variable of the same
 // meaning so a whole process can be flipped without code (STB_DECODE_SPLITK_LEGACY)
-enum Option { OPT_DECODE_SPLITK_LEGACY = 0, OPT_COUNT };
+enum Option { OPT_DECODE_SPLITK_LEGACY = 0, OPT_DECODE_LIN_PRIORITY, OPT_COUNT };
 int option(Option o);
+// launch priority of the kernels launched next by this host thread (cudaLaunchAttributePriority; 0 = the stream's own).
+// The decode step raises it for its latency-bound linear layers, so that -- when two half-batches are stepped on two streams --
+// the block scheduler serves a pending linear before the other half's remaining cross-attention CTAs.
+int& launch_priority();
 
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
@@ -87,11 +91,20 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int n = 0;
+    if (pdl_enabled()) {
+        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    if (launch_priority() != 0) {
+        attr[n].id = cudaLaunchAttributePriority;
+        attr[n].val.priority = launch_priority();
+        ++n;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -259,8 +259,8 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
         }
         part[2 + threadIdx.x] = o;
         if (threadIdx.x == 0) { part[0] = M; part[1] = Lsum; }
+        __threadfence();                                     // (the writers only: the other two warps have nothing to publish)
     }
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const int t = atomicAdd(tickets + b * H + h, 1);

@@ -334,15 +334,25 @@ static int launch_dl(const TmapVal& wh, const TmapVal& wl, const TmapVal& xh, co
     cfg.blockDim = dim3(192);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)split;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[3];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = (unsigned)split;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    if (launch_priority() != 0) {
+        attr[na].id = cudaLaunchAttributePriority;
+        attr[na].val.priority = launch_priority();
+        ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cfg.numAttrs = na;
     {
         const double wbytes = (double)g.n * g.kb_total * 64 * 2.0 * Cfg::NPL;
         ProfScope ps("decode_linear", st, wbytes + (double)g.B * g.kb_total * 64 * 2.0 * Cfg::NPL + (double)g.B * g.n * 4.0,

@@ -443,8 +443,11 @@ static size_t decode_state_bytes(const stb_model* m, int B, int cache_rows) {
 
 // seq_off (nullable) [B]: first cache row of each sequence; cache_rows: rows per sequence of the K/V caches (>= n_text_ctx
 // when ragged initial tokens are right-aligned, so that the shortest sequence still reaches its own n_text_ctx positions)
+// kv_total / kv_off: the cross K/V block was built for kv_total windows and this step's B sequences are its windows
+// [kv_off, kv_off + B) -- a batch can be stepped as two halves on two streams over ONE block (decode.py: DualStepEngine)
 static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos, const int32_t* seq_off, int cache_rows,
-                       const void* ckv, void* state, float* logits, long long ld_logits, void* ws, cudaStream_t st) {
+                       const void* ckv, int kv_total, int kv_off, void* state, float* logits, long long ld_logits, void* ws,
+                       cudaStream_t st) {
     const stb_dims& D = m->dims;
     const int d = D.n_text_state, H = D.n_text_head, ctx = cache_rows;
     const void* const(*t)[2] = m->t;
@@ -465,9 +468,20 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     const bool legacy_splitk = option(OPT_DECODE_SPLITK_LEGACY) != 0;
     const Split none = {nullptr, nullptr};
     // ln_g != nullptr: also produce LayerNorm(out)*ln_g+ln_b into w.ln (only with a residual, out_f32 = w.x)
+    int lin_priority = 0;
+    if (option(OPT_DECODE_LIN_PRIORITY) != 0) {
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess) lin_priority = greatest;   // e.g. -5
+    }
+    struct PriorityScope {                                     // the linears (and their fused finish / LayerNorm) only
+        int saved;
+        explicit PriorityScope(int p) : saved(launch_priority()) { launch_priority() = p; }
+        ~PriorityScope() { launch_priority() = saved; }
+    };
     auto lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
                    const float* res, float* out_f32, Split out_split, long long ld, const float* ln_g,
                    const float* ln_b) -> int {
+        PriorityScope prio(lin_priority);
         if (use_gemv) {
             STB_TRY(gemv(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st));
         } else if (use_splitk && !legacy_splitk && k % 64 == 0 && n >= 128) {
@@ -535,7 +549,9 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
                     none, d, nullptr, nullptr));
         Split Kx, vTx;
         CrossDecodeKV Vd;
-        cross_ptrs(m, B, ckv, l, Kx, vTx, &Vd);
+        cross_ptrs(m, kv_total, ckv, l, Kx, vTx, &Vd);
+        Vd.k_hi += (size_t)kv_off * H * STB_N_AUDIO_CTX * 64;
+        Vd.v_hi += (size_t)kv_off * H * STB_N_AUDIO_CTX * 64;
         STB_TRY(decode_attn_cross(w.q, Vd, B, H, d, w.xpart, w.tickets, w.attn.hi, w.attn.lo, nullptr, st));
         STB_TRY(lin(w.attn, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d, W_F32(L, STB_L_COUT_B), STB_ACT_NONE, w.x,
                     w.x, none, d, W_F32(L, STB_L_MLP_LN_G), W_F32(L, STB_L_MLP_LN_B)));
@@ -680,8 +696,8 @@ extern "C" size_t stb_decode_state_bytes_rows(const stb_model* m, int B, int cac
 extern "C" size_t stb_decode_ws_bytes(const stb_model* m, int B) { return m ? stb::carve_step(m, B, nullptr).bytes : 0; }
 
 extern "C" int stb_decode_step_ragged(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const int32_t* seq_off,
-                                      int cache_rows, const void* cross_kv, void* state, float* logits_out, long long ld_logits,
-                                      void* ws, size_t ws_bytes, void* stream) {
+                                      int cache_rows, const void* cross_kv, int kv_total, int kv_off, void* state,
+                                      float* logits_out, long long ld_logits, void* ws, size_t ws_bytes, void* stream) {
     STB_REQUIRE(m && tokens_in && pos && cross_kv && state && logits_out && ws && B >= 1, "stb_decode_step: bad arguments");
     STB_REQUIRE(ld_logits >= m->dims.n_vocab && ld_logits % 4 == 0, "stb_decode_step: ld_logits must be >= n_vocab and a multiple of 4");
     STB_REQUIRE(m->dims.n_text_ctx <= 448, "stb_decode_step: n_text_ctx > 448 unsupported");
@@ -689,12 +705,16 @@ extern "C" int stb_decode_step_ragged(stb_model* m, const int32_t* tokens_in, in
                 "stb_decode_step: cache_rows must be in [n_text_ctx, 2 n_text_ctx]");
     STB_TRY(check_weights(m, false, true));
     STB_REQUIRE(ws_bytes >= stb_decode_ws_bytes(m, B), "stb_decode_step: workspace too small");
-    return stb::decode_step(m, tokens_in, B, pos, seq_off, cache_rows, cross_kv, state, logits_out, ld_logits, ws, (cudaStream_t)stream);
+    if (kv_total <= 0) { kv_total = B; kv_off = 0; }
+    STB_REQUIRE(kv_off >= 0 && kv_off + B <= kv_total, "stb_decode_step: windows [%d, %d) outside the cross K/V block of %d", kv_off,
+                kv_off + B, kv_total);
+    return stb::decode_step(m, tokens_in, B, pos, seq_off, cache_rows, cross_kv, kv_total, kv_off, state, logits_out, ld_logits, ws,
+                            (cudaStream_t)stream);
 }
 
 extern "C" int stb_decode_step(stb_model* m, const int32_t* tokens_in, int B, int32_t* pos, const void* cross_kv, void* state,
                                float* logits_out, long long ld_logits, void* ws, size_t ws_bytes, void* stream) {
     STB_REQUIRE(m, "stb_decode_step: bad arguments");
-    return stb_decode_step_ragged(m, tokens_in, B, pos, nullptr, m->dims.n_text_ctx, cross_kv, state, logits_out, ld_logits, ws,
-                                  ws_bytes, stream);
+    return stb_decode_step_ragged(m, tokens_in, B, pos, nullptr, m->dims.n_text_ctx, cross_kv, B, 0, state, logits_out, ld_logits,
+                                  ws, ws_bytes, stream);
 }

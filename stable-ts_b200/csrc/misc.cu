@@ -60,6 +60,9 @@ static const OptDef g_opt_defs[OPT_COUNT] = {
     // 1: decode-step linears as round 1 ran them (swapped split-K GEMM with partials in L2 + finish kernel) instead of the
     // cluster kernel of decode_linear.cu -- kept for A/B timing of the two paths on the same box
     {"decode_splitk_legacy", "STB_DECODE_SPLITK_LEGACY", 0},
+    // 1: the decode step launches its linear layers with the device's greatest launch priority (matters only when two
+    // half-batches are stepped concurrently on two streams)
+    {"decode_lin_priority", "STB_DECODE_LIN_PRIORITY", 1},
 };
 static int g_opt[OPT_COUNT];
 static bool g_opt_init = false;
@@ -74,6 +77,11 @@ static void opt_init() {
 int option(Option o) {
     opt_init();
     return g_opt[o];
+}
+
+int& launch_priority() {
+    static thread_local int p = 0;
+    return p;
 }
 
 int sm_count() {

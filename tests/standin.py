@@ -141,6 +141,10 @@ class OracleStepEngine:
     def reset(self):
         pass
 
+    def step(self, ckv, *sample_args):
+        self.sample(*sample_args)
+        self.feed(self.next, ckv)
+
     @torch.no_grad()
     def feed(self, tokens, ckv):
         om, V, p = self.m.om, self.m.dims.n_vocab, int(self.pos)
