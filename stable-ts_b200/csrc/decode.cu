@@ -131,11 +131,16 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
 // the 16 lane groups merged through shared memory; each CTA writes (m, l, acc[64]) and the last CTA of a (b,h) to finish
 // (atomic ticket) merges the XS partials and writes the output.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int XS = 8;                       // key splits per (sequence, head)
-constexpr int XS_KEYS = 188;                // keys per split (8 x 188 = 1504 >= 1500)
-constexpr int XC = 2;                       // bulk-copy chunks per split (compute starts when the first one lands)
-constexpr int XC_KEYS = 94;
-constexpr int X_SMEM = XC * 2 * XC_KEYS * 128;   // K | V per chunk: 48128 B
+// key splits per (sequence, head): 8 (two 94-key chunks per CTA, 4 CTAs per SM) or 16 (one chunk, 8 CTAs per SM: twice the
+// warps to hide latency with the same bytes in flight, twice the partials to merge) -- option "xattn_splits"
+constexpr int XS_MAX = 16;
+constexpr int XC_KEYS = 94;                 // keys per bulk-copy chunk (16 x 94 = 1504 >= 1500)
+template <int NS> struct XCfg {
+    static constexpr int XS = NS;
+    static constexpr int XC = XS_MAX / NS;                  // chunks per split: compute starts when the first one lands
+    static constexpr int XS_KEYS = XC * XC_KEYS;            // keys per split
+    static constexpr int SMEM = XC * 2 * XC_KEYS * 128;     // K | V per chunk
+};
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -153,10 +158,12 @@ __device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
     }
 }
 
-__global__ void __launch_bounds__(128, 4)
+template <int NS>
+__global__ void __launch_bounds__(128, NS == 8 ? 4 : 8)
 decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const __half* __restrict__ v_hi, int d,
                          int T, float* __restrict__ partial, int* __restrict__ tickets, __half* __restrict__ out_hi,
                          __half* __restrict__ out_lo, float* __restrict__ out_f32) {
+    constexpr int XS = XCfg<NS>::XS, XC = XCfg<NS>::XC, XS_KEYS = XCfg<NS>::XS_KEYS;
     extern __shared__ __align__(128) uint8_t x_smem[];       // [chunk][K rows | V rows][XC_KEYS][128 B]
     __shared__ __align__(8) uint64_t s_bar[XC];
     __shared__ float s_m[4][4], s_l[4][4];
@@ -555,24 +562,30 @@ int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d
     STB_LAUNCH_OK();
     return STB_OK;
 }
-int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
-                      __half* ol, float* of, cudaStream_t st) {
-    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0);
+template <int NS>
+static int launch_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
+                        __half* ol, float* of, cudaStream_t st) {
     static bool attr_set[64] = {};                          // per device ordinal
     int dev = 0;
     STB_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM));
-        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, XCfg<NS>::SMEM));
+        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel<NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[dev] = true;
     }
-    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel, dim3(XS, H, B), dim3(128), (size_t)X_SMEM, st, q, kv.k_hi, kv.v_hi, d,
-                           (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
+    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<NS>, dim3(NS, H, B), dim3(128), (size_t)XCfg<NS>::SMEM, st, q, kv.k_hi, kv.v_hi,
+                           d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
     STB_LAUNCH_OK();
     return STB_OK;
 }
-size_t decode_cross_scratch_bytes(int B, int H) { return (size_t)B * H * XS * 66 * sizeof(float) + (size_t)B * H * sizeof(int) + 256; }
-int decode_cross_splits() { return XS; }
+int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
+                      __half* ol, float* of, cudaStream_t st) {
+    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0);
+    return decode_cross_splits() == 16 ? launch_cross<16>(q, kv, B, H, d, partial, tickets, oh, ol, of, st)
+                                       : launch_cross<8>(q, kv, B, H, d, partial, tickets, oh, ol, of, st);
+}
+size_t decode_cross_scratch_bytes(int B, int H) { return (size_t)B * H * XS_MAX * 66 * sizeof(float) + (size_t)B * H * sizeof(int) + 256; }
+int decode_cross_splits() { return option(OPT_XATTN_SPLITS) == 16 ? 16 : 8; }
 int v_headmajor(const __half* vT_hi, int BH, int T, int Tp, __half* v_hi, cudaStream_t st) {
     ProfScope ps("v_headmajor", st, (double)BH * T * 64 * 4.0);
     v_headmajor_kernel<<<dim3(cdiv(T, 64), BH), 256, 0, st>>>(vT_hi, T, Tp, v_hi);

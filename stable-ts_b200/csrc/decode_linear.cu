@@ -327,6 +327,7 @@ static int launch_dl(const TmapVal& wh, const TmapVal& wl, const TmapVal& xh, co
         STB_CUDA_OK(cudaFuncSetAttribute(decode_linear_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set[dev] = true;
     }
+    prefer_max_carveout(reinterpret_cast<const void*>(decode_linear_kernel<BN, PASSES>));
     const int mt = cdiv(g.n, 128);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));

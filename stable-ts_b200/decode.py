@@ -22,10 +22,13 @@ DUAL_MIN_BATCH = 32          # below this a step is pure launch latency and two 
 
 
 def dual_streams() -> int:
-    """Number of concurrent chains a large batch is stepped as (``DualStepEngine``): STB_DECODE_DUAL = 0 / 1 (one chain, one
-    stream), 2 (default: two halves on two streams), 3, ..."""
+    """Number of concurrent chains a large batch is stepped as (``DualStepEngine``): STB_DECODE_DUAL = 0 / 1 (default: one
+    chain, one stream), 2 (two halves on two streams), 3, ...  Measured on a B200 at 120 large-v3 windows (profiles/r2e_*):
+    1.28 ms per 4-layer step as one chain, 1.35 / 1.47 ms as two (without / with the launch priority), 1.75 ms as three --
+    a linear CTA owns its SM's shared memory, so it cannot share an SM with the other chain's attention CTAs and the chains
+    serialise at kernel granularity while every kernel gets smaller.  Kept as an opt-in (parity-tested) experiment."""
     import os
-    v = os.environ.get("STB_DECODE_DUAL", "2")
+    v = os.environ.get("STB_DECODE_DUAL", "0")
     try:
         n = int(v)
     except ValueError:

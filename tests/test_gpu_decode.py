@@ -198,3 +198,27 @@ def test_large_width_step_paths_agree():
         rg, _ = decode_windows(gm, tk, encb, opt)                     # CUDA-graph replay of the same step
         for j in range(2 * rep):
             assert rg[j].tokens == r2[j % 2].tokens
+
+
+@pytest.mark.parametrize("chains", [2, 3])
+def test_batch_stepped_as_concurrent_chains_matches_one_chain(chains, monkeypatch):
+    """DualStepEngine (STB_DECODE_DUAL): the batch as 2 / 3 chains on separate streams over ONE cross K/V block
+    (stb_decode_step_ragged kv_total / kv_off), captured into one graph -- same tokens and log-probs as the single chain."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import stable_path as SP
+    from oracle.whisper_ref.model import ModelDimensions
+    from stable_ts_b200.decode import DecodingOptions, decode_windows
+    dims = ModelDimensions(n_mels=80, n_audio_ctx=1500, n_audio_state=384, n_audio_head=6, n_audio_layer=2, n_vocab=51864,
+                           n_text_ctx=448, n_text_state=384, n_text_head=6, n_text_layer=3)
+    W, model, gm, tk = _mk(dims, 23)
+    audios = torch.stack([SP.synth_audio(480000, seed=300 + i) for i in range(7)]).repeat(6, 1)       # 42 windows
+    enc = gm.encode(gm.log_mel(audios.cuda()))
+    opt = DecodingOptions(sample_len=12)
+    monkeypatch.setenv("STB_DECODE_DUAL", "0")
+    one, _ = decode_windows(gm, tk, enc, opt)
+    monkeypatch.setenv("STB_DECODE_DUAL", str(chains))
+    many, ex = decode_windows(gm, tk, enc, opt)
+    for a, b in zip(one, many):
+        assert a.tokens == b.tokens and abs(a.avg_logprob - b.avg_logprob) < 1e-5
+        assert abs(a.no_speech_prob - b.no_speech_prob) <= 1e-6 + 1e-4 * a.no_speech_prob
