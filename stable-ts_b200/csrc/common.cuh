@@ -73,24 +73,18 @@ int sm_count();   // cached cudaDevAttrMultiProcessorCount of the current device
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-bool pdl_enabled();   // STB_PDL=0 disables (misc.cu)
+bool pdl_enabled(int kind = 0);   // STB_PDL bit mask (misc.cu): kind 0 = ordinary kernels, 1 = decode_linear
 // run-time switches (stb_set_option / stb_get_option, misc.cu); defaults come from the environment variable of the same
 // meaning so a whole process can be flipped without code (STB_DECODE_SPLITK_LEGACY)
-enum Option { OPT_DECODE_SPLITK_LEGACY = 0, OPT_DECODE_LIN_PRIORITY, OPT_UNIFORM_CARVEOUT, OPT_XATTN_SPLITS, OPT_COUNT };
+enum Option { OPT_DECODE_SPLITK_LEGACY = 0, OPT_DECODE_LIN_PRIORITY, OPT_COUNT };
 int option(Option o);
 // launch priority of the kernels launched next by this host thread (cudaLaunchAttributePriority; 0 = the stream's own).
 // The decode step raises it for its latency-bound linear layers, so that -- when two half-batches are stepped on two streams --
 // the block scheduler serves a pending linear before the other half's remaining cross-attention CTAs.
 int& launch_priority();
 
-// Every kernel of this library prefers the maximum shared-memory carveout: consecutive kernels of the decode step would
-// otherwise alternate between carveouts (200 KB GEMM tiles, 4 x 47 KB attention CTAs, LayerNorm with none), and an SM only
-// changes its L1 / shared split when it is idle -- a drain between every two launches of a ~10-launch-per-layer chain.
-void prefer_max_carveout(const void* kernel);   // misc.cu: once per (kernel, device)
-
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    prefer_max_carveout(reinterpret_cast<const void*>(kernel));
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = grid;

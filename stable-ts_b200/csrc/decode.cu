@@ -16,6 +16,10 @@
 
 namespace stb {
 
+// softmax in base 2: exp(x) = 2^(x log2 e); q is pre-scaled by log2 e, so every exponential of the attention kernels is one
+// exp2f (MUFU.EX2 + range fix-up) instead of expf's multiply + range reduction, executed per key by all 8 lanes of a group
+constexpr float LOG2E_F = 1.4426950408889634f;
+
 // ---------------------------------------------------------------------------------------------------------
 // self-attention over the fp32 K/V cache.  grid (H, B), 128 threads.
 //   qkv [B][3d] fp32 (q | k | v of the newest token); caches Kc, Vc [B][ctx][d] fp32; out split [B][d].
@@ -46,7 +50,7 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
     else vc[(long long)pos * d + (tid - 64)] = row[2 * d + h * 64 + (tid - 64)];
     float qr[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) qr[e] = row[h * 64 + sub * 8 + e] * 0.125f;
+    for (int e = 0; e < 8; ++e) qr[e] = row[h * 64 + sub * 8 + e] * (0.125f * LOG2E_F);   // scores in log2 units: exp2f below
     __syncthreads();                                         // the newest K / V row is visible to the whole CTA
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
@@ -76,8 +80,8 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
             s += __shfl_xor_sync(0xffffffffu, s, 4);
             if (j < n) {                                      // uniform within the 8-lane group
                 const float mn = fmaxf(m, s);
-                const float corr = expf(m - mn);              // exp(-inf) = 0 on the first key
-                const float p = expf(s - mn);
+                const float corr = exp2f(m - mn);              // exp(-inf) = 0 on the first key
+                const float p = exp2f(s - mn);
                 l = l * corr + p;
                 acc[0] = fmaf(p, va[u].x, acc[0] * corr); acc[1] = fmaf(p, va[u].y, acc[1] * corr);
                 acc[2] = fmaf(p, va[u].z, acc[2] * corr); acc[3] = fmaf(p, va[u].w, acc[3] * corr);
@@ -100,7 +104,7 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float mi = s_m[i >> 2][i & 3];
-            const float sc = (mi == -INFINITY) ? 0.f : expf(mi - M);
+            const float sc = (mi == -INFINITY) ? 0.f : exp2f(mi - M);
             Lsum += s_l[i >> 2][i & 3] * sc;
             o += s_acc[i >> 2][i & 3][tid] * sc;
         }
@@ -131,16 +135,12 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
 // the 16 lane groups merged through shared memory; each CTA writes (m, l, acc[64]) and the last CTA of a (b,h) to finish
 // (atomic ticket) merges the XS partials and writes the output.
 // ---------------------------------------------------------------------------------------------------------
-// key splits per (sequence, head): 8 (two 94-key chunks per CTA, 4 CTAs per SM) or 16 (one chunk, 8 CTAs per SM: twice the
-// warps to hide latency with the same bytes in flight, twice the partials to merge) -- option "xattn_splits"
-constexpr int XS_MAX = 16;
-constexpr int XC_KEYS = 94;                 // keys per bulk-copy chunk (16 x 94 = 1504 >= 1500)
-template <int NS> struct XCfg {
-    static constexpr int XS = NS;
-    static constexpr int XC = XS_MAX / NS;                  // chunks per split: compute starts when the first one lands
-    static constexpr int XS_KEYS = XC * XC_KEYS;            // keys per split
-    static constexpr int SMEM = XC * 2 * XC_KEYS * 128;     // K | V per chunk
-};
+constexpr int XS = 8;                       // key splits per (sequence, head)  (16 splits, i.e. 8 CTAs per SM with one chunk
+                                            //  each, measured slower: 191 vs 178 us per launch, profiles/r2f_summary.txt)
+constexpr int XS_KEYS = 188;                // keys per split (8 x 188 = 1504 >= 1500)
+constexpr int XC = 2;                       // bulk-copy chunks per split (compute starts when the first one lands)
+constexpr int XC_KEYS = 94;
+constexpr int X_SMEM = XC * 2 * XC_KEYS * 128;   // K | V per chunk: 48128 B
 
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -158,12 +158,10 @@ __device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
     }
 }
 
-template <int NS>
-__global__ void __launch_bounds__(128, NS == 8 ? 4 : 8)
+__global__ void __launch_bounds__(128, 4)
 decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__ k_hi, const __half* __restrict__ v_hi, int d,
                          int T, float* __restrict__ partial, int* __restrict__ tickets, __half* __restrict__ out_hi,
                          __half* __restrict__ out_lo, float* __restrict__ out_f32) {
-    constexpr int XS = XCfg<NS>::XS, XC = XCfg<NS>::XC, XS_KEYS = XCfg<NS>::XS_KEYS;
     extern __shared__ __align__(128) uint8_t x_smem[];       // [chunk][K rows | V rows][XC_KEYS][128 B]
     __shared__ __align__(8) uint64_t s_bar[XC];
     __shared__ float s_m[4][4], s_l[4][4];
@@ -198,7 +196,7 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
     pdl_wait();                                              // q comes from the preceding linear
     float qr[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e] * 0.125f;
+    for (int e = 0; e < 8; ++e) qr[e] = q[(long long)b * d + h * 64 + sub * 8 + e] * (0.125f * LOG2E_F);   // log2 units
     float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -230,13 +228,13 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
                 sc[u] = ok ? s : -INFINITY;
             }
             const float mn = fmaxf(fmaxf(m, sc[0]), fmaxf(fmaxf(sc[1], sc[2]), sc[3]));   // key u = 0 is valid: finite
-            const float corr = expf(m - mn);                  // exp(-inf) = 0 for the first block
+            const float corr = exp2f(m - mn);                  // exp(-inf) = 0 for the first block
             l *= corr;
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] *= corr;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const float p = expf(sc[u] - mn);             // 0 for keys past the chunk
+                const float p = exp2f(sc[u] - mn);             // 0 for keys past the chunk
                 float vf[8];
                 unpack8(vh[u], vf);
                 l += p;
@@ -260,7 +258,7 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const float mi = s_m[i >> 2][i & 3];
-            const float sc = (mi == -INFINITY) ? 0.f : expf(mi - M);
+            const float sc = (mi == -INFINITY) ? 0.f : exp2f(mi - M);
             Lsum += s_l[i >> 2][i & 3] * sc;
             o += s_acc[i >> 2][i & 3][threadIdx.x] * sc;
         }
@@ -285,7 +283,7 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
 #pragma unroll
         for (int i = 0; i < XS; ++i) {
             const float mi = __ldcg(p0 + i * 66);
-            const float sc = (mi == -INFINITY) ? 0.f : expf(mi - M);
+            const float sc = (mi == -INFINITY) ? 0.f : exp2f(mi - M);
             Lsum += __ldcg(p0 + i * 66 + 1) * sc;
             o += __ldcg(p0 + i * 66 + 2 + threadIdx.x) * sc;
         }
@@ -562,30 +560,24 @@ int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d
     STB_LAUNCH_OK();
     return STB_OK;
 }
-template <int NS>
-static int launch_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
-                        __half* ol, float* of, cudaStream_t st) {
+int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
+                      __half* ol, float* of, cudaStream_t st) {
+    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0);
     static bool attr_set[64] = {};                          // per device ordinal
     int dev = 0;
     STB_CUDA_OK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, XCfg<NS>::SMEM));
-        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel<NS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM));
+        STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[dev] = true;
     }
-    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel<NS>, dim3(NS, H, B), dim3(128), (size_t)XCfg<NS>::SMEM, st, q, kv.k_hi, kv.v_hi,
-                           d, (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
+    STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel, dim3(XS, H, B), dim3(128), (size_t)X_SMEM, st, q, kv.k_hi, kv.v_hi, d,
+                           (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));
     STB_LAUNCH_OK();
     return STB_OK;
 }
-int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int d, float* partial, int* tickets, __half* oh,
-                      __half* ol, float* of, cudaStream_t st) {
-    ProfScope ps("decode_cross_attn", st, (double)B * H * 2.0 * STB_N_AUDIO_CTX * 64 * 2.0);
-    return decode_cross_splits() == 16 ? launch_cross<16>(q, kv, B, H, d, partial, tickets, oh, ol, of, st)
-                                       : launch_cross<8>(q, kv, B, H, d, partial, tickets, oh, ol, of, st);
-}
-size_t decode_cross_scratch_bytes(int B, int H) { return (size_t)B * H * XS_MAX * 66 * sizeof(float) + (size_t)B * H * sizeof(int) + 256; }
-int decode_cross_splits() { return option(OPT_XATTN_SPLITS) == 16 ? 16 : 8; }
+size_t decode_cross_scratch_bytes(int B, int H) { return (size_t)B * H * XS * 66 * sizeof(float) + (size_t)B * H * sizeof(int) + 256; }
+int decode_cross_splits() { return XS; }
 int v_headmajor(const __half* vT_hi, int BH, int T, int Tp, __half* v_hi, cudaStream_t st) {
     ProfScope ps("v_headmajor", st, (double)BH * T * 64 * 4.0);
     v_headmajor_kernel<<<dim3(cdiv(T, 64), BH), 256, 0, st>>>(vT_hi, T, Tp, v_hi);

@@ -327,7 +327,6 @@ static int launch_dl(const TmapVal& wh, const TmapVal& wl, const TmapVal& xh, co
         STB_CUDA_OK(cudaFuncSetAttribute(decode_linear_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
         attr_set[dev] = true;
     }
-    prefer_max_carveout(reinterpret_cast<const void*>(decode_linear_kernel<BN, PASSES>));
     const int mt = cdiv(g.n, 128);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
@@ -342,7 +341,7 @@ static int launch_dl(const TmapVal& wh, const TmapVal& wl, const TmapVal& xh, co
     attr[na].val.clusterDim.y = 1;
     attr[na].val.clusterDim.z = 1;
     ++na;
-    if (pdl_enabled()) {
+    if (pdl_enabled(1)) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;

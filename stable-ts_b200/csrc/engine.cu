@@ -428,7 +428,7 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.x = c.take<float>((size_t)B * d);
     w.qkv = c.take<float>((size_t)B * 3 * d);
     w.q = c.take<float>((size_t)B * d);
-    w.xpart = c.take<float>((size_t)B * m->dims.n_text_head * 16 * 66);            // up to 16 key splits (decode.cu XS_MAX)
+    w.xpart = c.take<float>((size_t)B * m->dims.n_text_head * decode_cross_splits() * 66);
     w.tickets = c.take<int>((size_t)B * m->dims.n_text_head);
     w.ln = take_split(c, (size_t)B * d, lo);
     w.attn = take_split(c, (size_t)B * d, lo);

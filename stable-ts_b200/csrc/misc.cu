@@ -4,9 +4,6 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <mutex>
-#include <set>
-#include <utility>
 #include <map>
 #include <string>
 #include <vector>
@@ -50,13 +47,15 @@ ProfScope::~ProfScope() {
     if (slot >= 0) cudaEventRecord(g_prof[slot].e1, st);
 }
 
-bool pdl_enabled() {
+// STB_PDL: bit 0 = programmatic dependent launch for the ordinary kernels (launch_pdl), bit 1 = for the cluster kernel of
+// the decode-step linears.  Default 3 (both); 0 disables it everywhere (the in-kernel griddepcontrol instructions are then no-ops).
+bool pdl_enabled(int kind) {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("STB_PDL");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = (e && e[0]) ? atoi(e) : 3;
     }
-    return v != 0;
+    return (v >> kind) & 1;
 }
 
 struct OptDef { const char* name; const char* env; int dflt; };
@@ -67,11 +66,6 @@ static const OptDef g_opt_defs[OPT_COUNT] = {
     // 1: the decode step launches its linear layers with the device's greatest launch priority (matters only when two
     // half-batches are stepped concurrently on two streams)
     {"decode_lin_priority", "STB_DECODE_LIN_PRIORITY", 1},
-    // 1: every kernel launched through launch_pdl asks for the maximum shared-memory carveout (no L1/shared reconfiguration
-    // between the kernels of the decode step)
-    {"uniform_carveout", "STB_UNIFORM_CARVEOUT", 1},
-    // key splits per (sequence, head) of the decode-step cross-attention: 8 or 16
-    {"xattn_splits", "STB_XATTN_SPLITS", 8},
 };
 static int g_opt[OPT_COUNT];
 static bool g_opt_init = false;
@@ -86,17 +80,6 @@ static void opt_init() {
 int option(Option o) {
     opt_init();
     return g_opt[o];
-}
-
-void prefer_max_carveout(const void* kernel) {
-    static std::mutex mu;
-    static std::set<std::pair<const void*, int>> done;
-    if (option(OPT_UNIFORM_CARVEOUT) == 0) return;
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return;
-    std::lock_guard<std::mutex> lock(mu);
-    if (done.insert({kernel, dev}).second)
-        (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 int& launch_priority() {
