@@ -20,15 +20,27 @@ namespace stb {
 // exp2f (MUFU.EX2 + range fix-up) instead of expf's multiply + range reduction, executed per key by all 8 lanes of a group
 constexpr float LOG2E_F = 1.4426950408889634f;
 
+__device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
+    const __half2* h = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 t = __half22float2(h[e]);
+        f[2 * e] = t.x;
+        f[2 * e + 1] = t.y;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
-// self-attention over the fp32 K/V cache.  grid (H, B), 128 threads.
-//   qkv [B][3d] fp32 (q | k | v of the newest token); caches Kc, Vc [B][ctx][d] fp32; out split [B][d].
+// self-attention over the fp16 K/V cache.  grid (H, B), 128 threads.
+//   qkv [B][3d] fp32 (q | k | v of the newest token); caches Kc, Vc [B][ctx][d] fp16; out split [B][d].
+// The cache holds fp16 like the cross K/V of the step (q stays fp32): measured at 32 layers against the fp32 oracle the step
+// logits move from 2.1e-5 to the figure in DESIGN.md section 2 (gate 1e-3), for half the bytes of the second-largest stream.
 // One pass, flash-decoding style (same lane mapping as the cross-attention kernel below): 8 lanes share a key row
 // (2 x 16-byte loads of K and of V per lane), 4 keys per warp load, 4 keys in flight per lane group, online softmax per
 // lane group, the 16 lane groups of the CTA merged through shared memory.
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, float* __restrict__ Vc, int d, int ctx,
+decode_self_attn_kernel(const float* __restrict__ qkv, __half* __restrict__ Kc, __half* __restrict__ Vc, int d, int ctx,
                         const int32_t* __restrict__ pos_ptr, const int32_t* __restrict__ seq_off, __half* __restrict__ out_hi,
                         __half* __restrict__ out_lo, float* __restrict__ out_f32) {
     __shared__ float s_m[4][4], s_l[4][4];
@@ -44,10 +56,10 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
     // sequence b's own tokens occupy cache rows [seq_off[b], pos]; earlier rows hold idle steps and are never attended
     const int first_row = seq_off != nullptr ? min(seq_off[b], pos) : 0;
     const float* row = qkv + (long long)b * 3 * d;
-    float* kc = Kc + (long long)b * ctx * d + h * 64;
-    float* vc = Vc + (long long)b * ctx * d + h * 64;
-    if (tid < 64) kc[(long long)pos * d + tid] = row[d + h * 64 + tid];
-    else vc[(long long)pos * d + (tid - 64)] = row[2 * d + h * 64 + (tid - 64)];
+    __half* kc = Kc + (long long)b * ctx * d + h * 64;
+    __half* vc = Vc + (long long)b * ctx * d + h * 64;
+    if (tid < 64) kc[(long long)pos * d + tid] = __float2half_rn(row[d + h * 64 + tid]);
+    else vc[(long long)pos * d + (tid - 64)] = __float2half_rn(row[2 * d + h * 64 + (tid - 64)]);
     float qr[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) qr[e] = row[h * 64 + sub * 8 + e] * (0.125f * LOG2E_F);   // scores in log2 units: exp2f below
@@ -57,24 +69,24 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     for (int base = first_row; base < n; base += 64) {       // block-uniform trip count: 64 keys per CTA iteration
         const int j0 = base + w * 4 + grp;
-        float4 ka[4], kb[4], va[4], vb[4];
+        uint4 kh[4], vh[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u * 16;
-            ka[u] = kb[u] = va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            kh[u] = vh[u] = make_uint4(0u, 0u, 0u, 0u);
             if (j < n) {
-                const float4* kr = reinterpret_cast<const float4*>(kc + (long long)j * d + sub * 8);
-                const float4* vr = reinterpret_cast<const float4*>(vc + (long long)j * d + sub * 8);
-                ka[u] = kr[0]; kb[u] = kr[1];
-                va[u] = vr[0]; vb[u] = vr[1];
+                kh[u] = *reinterpret_cast<const uint4*>(kc + (long long)j * d + sub * 8);
+                vh[u] = *reinterpret_cast<const uint4*>(vc + (long long)j * d + sub * 8);
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int j = j0 + u * 16;
-            float s = qr[0] * ka[u].x;
-            s = fmaf(qr[1], ka[u].y, s); s = fmaf(qr[2], ka[u].z, s); s = fmaf(qr[3], ka[u].w, s);
-            s = fmaf(qr[4], kb[u].x, s); s = fmaf(qr[5], kb[u].y, s); s = fmaf(qr[6], kb[u].z, s); s = fmaf(qr[7], kb[u].w, s);
+            float kf[8];
+            unpack8(kh[u], kf);
+            float s = qr[0] * kf[0];
+#pragma unroll
+            for (int e = 1; e < 8; ++e) s = fmaf(qr[e], kf[e], s);
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -82,11 +94,11 @@ decode_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ Kc, f
                 const float mn = fmaxf(m, s);
                 const float corr = exp2f(m - mn);              // exp(-inf) = 0 on the first key
                 const float p = exp2f(s - mn);
+                float vf[8];
+                unpack8(vh[u], vf);
                 l = l * corr + p;
-                acc[0] = fmaf(p, va[u].x, acc[0] * corr); acc[1] = fmaf(p, va[u].y, acc[1] * corr);
-                acc[2] = fmaf(p, va[u].z, acc[2] * corr); acc[3] = fmaf(p, va[u].w, acc[3] * corr);
-                acc[4] = fmaf(p, vb[u].x, acc[4] * corr); acc[5] = fmaf(p, vb[u].y, acc[5] * corr);
-                acc[6] = fmaf(p, vb[u].z, acc[6] * corr); acc[7] = fmaf(p, vb[u].w, acc[7] * corr);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] = fmaf(p, vf[e], acc[e] * corr);
                 m = mn;
             }
         }
@@ -146,16 +158,6 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-
-__device__ __forceinline__ void unpack8(const uint4& a, float (&f)[8]) {
-    const __half2* h = reinterpret_cast<const __half2*>(&a);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float2 t = __half22float2(h[e]);
-        f[2 * e] = t.x;
-        f[2 * e + 1] = t.y;
-    }
 }
 
 __global__ void __launch_bounds__(128, 4)
@@ -286,6 +288,216 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
             const float sc = (mi == -INFINITY) ? 0.f : exp2f(mi - M);
             Lsum += __ldcg(p0 + i * 66 + 1) * sc;
             o += __ldcg(p0 + i * 66 + 2 + threadIdx.x) * sc;
+        }
+        o /= Lsum;
+        const long long oo = (long long)b * d + h * 64 + threadIdx.x;
+        if (out_f32) out_f32[oo] = o;
+        if (out_hi) {
+            __half hi, lo;
+            split_f16(o, hi, lo);
+            out_hi[oo] = hi;
+            if (out_lo) out_lo[oo] = lo;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same cross-attention on the warp-level tensor cores (option "xattn_tc").  The scalar kernel above spends ~11 warp
+// instructions per key (fp16 -> fp32 unpacking, 8-lane shuffles, one exp per lane) and runs at 62 % issue utilisation while
+// it streams; here one query row costs ~150 warp instructions per 192 keys:
+//   * K and V tiles [96 keys][64] fp16 land through 2-D TMA copies with SWIZZLE_128B (zero fill past the last key), so
+//     ldmatrix reads them without bank conflicts;
+//   * scores: mma.sync m16n8k16, A = the query in rows 0 / 1 (fp16 hi / lo of q * log2(e) / 8: the fp32 query is
+//     represented to 2^-22), B = 8 keys per tile straight from ldmatrix; row 0 + row 1 = the fp32-grade score;
+//   * one exact softmax per CTA (max over its 192 keys through shared memory; partials of the 8 splits are merged as before);
+//   * P.V: mma.sync m16n8k8 per 8-key tile, A = p in rows 0 / 1 (hi / lo), B = V through ldmatrix.trans.
+// Warp w owns tiles w, w + 4, w + 8 of each 12-tile chunk.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int XT_KEYS = 96;                  // keys per chunk
+constexpr int XT_CHUNKS = 2;                 // chunks per split: 8 x 192 = 1536 >= 1500
+constexpr int XT_TILES = XT_KEYS / 8 / 4;    // 8-key tiles per warp per chunk
+constexpr int XT_SMEM = XT_CHUNKS * 2 * XT_KEYS * 128 + 1024;
+
+struct XPerm { int p[3]; };
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5}, {%6}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(0u), "r"(b0));
+}
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
+    __half2 h = __halves2half2(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128, 4)
+decode_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, const XPerm perm,
+                            const float* __restrict__ q, int d, int T, float* __restrict__ partial, int* __restrict__ tickets,
+                            __half* __restrict__ out_hi, __half* __restrict__ out_lo, float* __restrict__ out_f32) {
+    extern __shared__ uint8_t xt_dyn[];
+    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xt_dyn) + 1023) & ~uintptr_t(1023));
+    __shared__ __align__(8) uint64_t s_bar[XT_CHUNKS];
+    __shared__ float s_m[4], s_l[4];
+    __shared__ float s_acc[4][64];
+    __shared__ int s_last;
+    const int split = blockIdx.x, h = blockIdx.y, b = blockIdx.z, H = gridDim.y;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int key0 = split * (XT_CHUNKS * XT_KEYS);
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+#pragma unroll
+        for (int c = 0; c < XT_CHUNKS; ++c) mbar_init(&s_bar[c], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < XT_CHUNKS; ++c) {
+            int v[4] = {key0 + c * XT_KEYS, h, b, 0};
+            uint8_t* dst = sm + (size_t)c * 2 * XT_KEYS * 128;
+            mbar_arrive_expect_tx(&s_bar[c], 2u * XT_KEYS * 128u);       // the box is always transferred whole (zero fill past T)
+            tma_load_4d(dst, &tmK, &s_bar[c], 0, v[perm.p[0]], v[perm.p[1]], v[perm.p[2]]);
+            tma_load_4d(dst + XT_KEYS * 128, &tmV, &s_bar[c], 0, v[perm.p[0]], v[perm.p[1]], v[perm.p[2]]);
+        }
+    }
+    pdl_trigger();
+    pdl_wait();                                              // q comes from the preceding linear
+    // ---- query fragments: rows 0 / 1 of A hold the fp16 hi / lo parts of q * log2(e) / 8, every other row is zero
+    uint32_t qa0[4], qa2[4];
+    {
+        const float* qp = q + (long long)b * d + h * 64;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            __half hv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int idx = ks * 16 + 2 * t + (e & 1) + (e >> 1) * 8;
+                const float x = qp[idx] * (0.125f * LOG2E_F);
+                __half hi, lo;
+                split_f16(x, hi, lo);
+                hv[e] = g == 0 ? hi : (g == 1 ? lo : __float2half(0.f));
+            }
+            qa0[ks] = pack_h2(hv[0], hv[1]);
+            qa2[ks] = pack_h2(hv[2], hv[3]);
+        }
+    }
+    const uint32_t sm_base = smem_u32(sm);
+    const int mrow = lane & 7, mat = lane >> 3;              // ldmatrix: this lane addresses row `mrow` of matrix `mat`
+    // ---- scores of this warp's 6 tiles (lanes 0..3 end up with the two keys 2t, 2t + 1 of each tile)
+    float sc[XT_CHUNKS * XT_TILES][2];
+#pragma unroll
+    for (int c = 0; c < XT_CHUNKS; ++c) {
+        mbar_wait(&s_bar[c], 0, 40 + c);
+        const uint32_t kbase = sm_base + (uint32_t)(c * 2 * XT_KEYS * 128);
+#pragma unroll
+        for (int i = 0; i < XT_TILES; ++i) {
+            const int r0 = (w + 4 * i) * 8;
+            const int row = r0 + mrow;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {            // dims 0..31, 32..63: four 16-byte chunks each
+                uint32_t r[4];
+                ldsm_x4(r, kbase + (uint32_t)(row * 128) + (uint32_t)((((half * 4 + mat) ^ (row & 7)) << 4)));
+                mma_16816(acc, qa0[half * 2], qa2[half * 2], r[0], r[1]);
+                mma_16816(acc, qa0[half * 2 + 1], qa2[half * 2 + 1], r[2], r[3]);
+            }
+            // row 0 (lanes 0..3) + row 1 (lanes 4..7): hi and lo parts of the query
+            const float s0 = acc[0] + __shfl_down_sync(0xffffffffu, acc[0], 4);
+            const float s1 = acc[1] + __shfl_down_sync(0xffffffffu, acc[1], 4);
+            const int key = key0 + c * XT_KEYS + r0 + 2 * t;
+            sc[c * XT_TILES + i][0] = (g == 0 && key < T) ? s0 : -INFINITY;
+            sc[c * XT_TILES + i][1] = (g == 0 && key + 1 < T) ? s1 : -INFINITY;
+        }
+    }
+    // ---- exact softmax over the CTA's keys
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < XT_CHUNKS * XT_TILES; ++i) m = fmaxf(m, fmaxf(sc[i][0], sc[i][1]));
+    m = warp_max(m);
+    if (lane == 0) s_m[w] = m;
+    __syncthreads();
+    const float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+    float l = 0.f;
+    float oacc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < XT_CHUNKS; ++c) {
+        const uint32_t vbase = sm_base + (uint32_t)(c * 2 * XT_KEYS * 128 + XT_KEYS * 128);
+#pragma unroll
+        for (int i = 0; i < XT_TILES; ++i) {
+            const float p0 = (M == -INFINITY) ? 0.f : exp2f(sc[c * XT_TILES + i][0] - M);   // 0 for lanes / keys without a score
+            const float p1 = (M == -INFINITY) ? 0.f : exp2f(sc[c * XT_TILES + i][1] - M);
+            l += p0 + p1;
+            __half h0, l0, h1, l1;
+            split_f16(p0, h0, l0);
+            split_f16(p1, h1, l1);
+            const uint32_t hi = pack_h2(h0, h1), lo = pack_h2(l0, l1);
+            const uint32_t lo_up = __shfl_up_sync(0xffffffffu, lo, 4);   // row 1 (lanes 4..7) carries the lo parts
+            const uint32_t a0 = g == 0 ? hi : (g == 1 ? lo_up : 0u);
+            const int r0 = (w + 4 * i) * 8;
+            const int row = r0 + mrow;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[4];
+                ldsm_x4_t(r, vbase + (uint32_t)(row * 128) + (uint32_t)((((half * 4 + mat) ^ (row & 7)) << 4)));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) mma_1688(oacc[half * 4 + j], a0, r[j]);
+            }
+        }
+    }
+    // ---- per warp: row 0 + row 1 of every n-tile -> 64 output dims in lanes 0..3; then the 4 warps through shared memory
+    l = warp_sum(l);
+    if (lane == 0) s_l[w] = l;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const float o0 = oacc[nt][0] + __shfl_down_sync(0xffffffffu, oacc[nt][0], 4);
+        const float o1 = oacc[nt][1] + __shfl_down_sync(0xffffffffu, oacc[nt][1], 4);
+        if (g == 0) {
+            s_acc[w][nt * 8 + 2 * t] = o0;
+            s_acc[w][nt * 8 + 2 * t + 1] = o1;
+        }
+    }
+    __syncthreads();
+    float* part = partial + (((long long)b * H + h) * XS + split) * 66;
+    if (threadIdx.x < 64) {
+        part[2 + threadIdx.x] = (s_acc[0][threadIdx.x] + s_acc[1][threadIdx.x]) + (s_acc[2][threadIdx.x] + s_acc[3][threadIdx.x]);
+        if (threadIdx.x == 0) { part[0] = M; part[1] = (s_l[0] + s_l[1]) + (s_l[2] + s_l[3]); }
+        __threadfence();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int tk = atomicAdd(tickets + b * H + h, 1);
+        s_last = (tk == XS - 1);
+        if (s_last) tickets[b * H + h] = 0;                  // re-arm for the next launch
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 64) {
+        __threadfence();
+        const float* p0 = partial + ((long long)b * H + h) * XS * 66;
+        float Mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < XS; ++i) Mx = fmaxf(Mx, __ldcg(p0 + i * 66));
+        float Lsum = 0.f, o = 0.f;
+#pragma unroll
+        for (int i = 0; i < XS; ++i) {
+            const float mi = __ldcg(p0 + i * 66);
+            const float scl = (mi == -INFINITY) ? 0.f : exp2f(mi - Mx);
+            Lsum += __ldcg(p0 + i * 66 + 1) * scl;
+            o += __ldcg(p0 + i * 66 + 2 + threadIdx.x) * scl;
         }
         o /= Lsum;
         const long long oo = (long long)b * d + h * 64 + threadIdx.x;
@@ -553,7 +765,7 @@ extern "C" int stb_sample_greedy(float* logits, long long ld, int B, int V, int 
 }
 
 namespace stb {
-int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos,
+int decode_attn_self(const float* qkv, __half* Kc, __half* Vc, int B, int H, int d, int ctx, const int32_t* pos,
                      const int32_t* seq_off, __half* oh, __half* ol, float* of, cudaStream_t st) {
     ProfScope ps("decode_self_attn", st);
     STB_CUDA_OK(launch_pdl(decode_self_attn_kernel, dim3(H, B), dim3(128), 0, st, qkv, Kc, Vc, d, ctx, pos, seq_off, oh, ol, of));
@@ -570,6 +782,27 @@ int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int
         STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, X_SMEM));
         STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_set[dev] = true;
+    }
+    if (option(OPT_XATTN_TC) != 0) {
+        static bool attr_tc[64] = {};
+        if (dev >= 0 && dev < 64 && !attr_tc[dev]) {
+            STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XT_SMEM));
+            STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            attr_tc[dev] = true;
+        }
+        const int T = (int)STB_N_AUDIO_CTX;
+        TmapVal tk, tv;
+        STB_TRY(make_tmap(kv.k_hi, T, 64, H, B, 64, (long long)T * 64, (long long)H * T * 64, XT_KEYS, &tk));
+        STB_TRY(make_tmap(kv.v_hi, T, 64, H, B, 64, (long long)T * 64, (long long)H * T * 64, XT_KEYS, &tv));
+        XPerm perm;
+        for (int i = 0; i < 3; ++i) {
+            STB_REQUIRE(tk.perm[i] == tv.perm[i], "decode_attn_cross: K / V tensor maps disagree");
+            perm.p[i] = tk.perm[i];
+        }
+        STB_CUDA_OK(launch_pdl(decode_cross_attn_tc_kernel, dim3(XS, H, B), dim3(128), (size_t)XT_SMEM, st, tk.map, tv.map, perm, q, d,
+                               T, partial, tickets, oh, ol, of));
+        STB_LAUNCH_OK();
+        return STB_OK;
     }
     STB_CUDA_OK(launch_pdl(decode_cross_attn_kernel, dim3(XS, H, B), dim3(128), (size_t)X_SMEM, st, q, kv.k_hi, kv.v_hi, d,
                            (int)STB_N_AUDIO_CTX, partial, tickets, oh, ol, of));

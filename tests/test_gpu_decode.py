@@ -222,3 +222,49 @@ def test_batch_stepped_as_concurrent_chains_matches_one_chain(chains, monkeypatc
     for a, b in zip(one, many):
         assert a.tokens == b.tokens and abs(a.avg_logprob - b.avg_logprob) < 1e-5
         assert abs(a.no_speech_prob - b.no_speech_prob) <= 1e-6 + 1e-4 * a.no_speech_prob
+
+
+def test_cross_attention_tensor_core_variant():
+    """Option "xattn_tc": the decode-step cross-attention on mma.sync over TMA-swizzled tiles must give the step logits of the
+    scalar kernel (both fp32-grade in q, fp16 K / V) and the oracle's tokens."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import stable_path as SP
+    from oracle.whisper_ref.model import ModelDimensions
+    from stable_ts_b200 import _lib as L
+    from stable_ts_b200.decode import DecodingOptions, decode_windows
+    dims = ModelDimensions(n_mels=128, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=1, n_vocab=51866,
+                           n_text_ctx=448, n_text_state=1280, n_text_head=20, n_text_layer=2)
+    W, model, gm, tk = _mk(dims, 17)
+    audios = torch.stack([SP.synth_audio(480000, seed=90 + i) for i in range(3)])
+    audios[2, 200000:] = 0                                    # a window whose tail is silence
+    opt = DecodingOptions(sample_len=6)
+    V = dims.n_vocab
+    try:
+        for rep in (1, 14):                                   # B = 3 (GEMV path) and B = 42 (cluster linears)
+            enc = gm.encode(gm.log_mel(audios.repeat(rep, 1).cuda()))
+            L.set_option("xattn_tc", 0)
+            r0, x0 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
+            L.set_option("xattn_tc", 1)
+            r1, x1 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
+            worst = 0.0
+            for a, b in zip(x0["step_logits"], x1["step_logits"]):
+                a, b = a.float().cpu(), b.float().cpu()
+                fin = a > -1e30
+                assert torch.equal(fin, b > -1e30)
+                worst = max(worst, ((a[fin] - b[fin]).abs().max() / a[fin].abs().max()).item())
+            print(f"B={3 * rep}: tensor-core vs scalar cross-attention, worst step-logit rel diff {worst:.2e}")
+            assert worst < 2e-5
+            for a, b in zip(r0, r1):
+                assert a.tokens == b.tokens
+            rg, _ = decode_windows(gm, tk, enc, opt)          # graph replay with the option on
+            for a, b in zip(r0, rg):
+                assert a.tokens == b.tokens
+        # against the CPU oracle (tiny.en, free-running greedy)
+        W2, om, gm2, tk2 = _mk("tiny.en", 3)
+        audio = SP.synth_audio(480000, seed=7)
+        ref, _, _ = SP.decode_window(om, _mel(W2, om, audio), language="en", sample_len=16)
+        res, _ = decode_windows(gm2, tk2, gm2.encode(gm2.log_mel(audio.cuda()[None])), DecodingOptions(language="en", sample_len=16))
+        assert res[0].tokens == ref.tokens and abs(res[0].avg_logprob - ref.avg_logprob) < 1e-3
+    finally:
+        L.set_option("xattn_tc", 0)
