@@ -317,10 +317,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQh, const __grid_const
 template <int PASSES>
 static int launch_attention(const TmapVal (&tm)[6], AttnArgs& g, int n_batch, cudaStream_t st) {
     using Cfg = AttnCfg<PASSES>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};    // per device ordinal
+    int dev = 0;
+    STB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         STB_CUDA_OK(cudaFuncSetAttribute(attention_tc_kernel<PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     dim3 grid(cdiv(g.Mq, AT_BQ), g.H, n_batch);
     const double zz = (double)n_batch * g.H;

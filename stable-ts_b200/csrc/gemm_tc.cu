@@ -424,6 +424,8 @@ int make_tmap(const void* base, int rows, int k, int H, int B, long long rs, lon
     for (int i = 0; i < 3; ++i) v.perm[i] = d[i].id;
     {
         std::lock_guard<std::mutex> lk(g_tmap_mu);
+        // keyed by raw pointers: a long-lived process that keeps allocating new buffers would grow it without bound
+        if (g_tmap_cache.size() >= 16384) g_tmap_cache.clear();
         g_tmap_cache.emplace(key, v);
     }
     *out = v;
@@ -434,11 +436,13 @@ template <int BN, int PASSES>
 static int launch_gemm(const TmapVal& ah, const TmapVal& al, const TmapVal& bh, const TmapVal& bl, GemmArgs& g,
                        int n_batch, cudaStream_t st) {
     using Cfg = GemmCfg<BN, PASSES>;
-    static bool attr_set = false;     // per instantiation
-    if (!attr_set) {
+    static bool attr_set[64] = {};    // per instantiation and device ordinal (function attributes are per device)
+    int dev = 0;
+    STB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
         STB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, PASSES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::SMEM));
-        attr_set = true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
     for (int i = 0; i < 3; ++i) {
         g.permA[i] = ah.perm[i];
