@@ -261,7 +261,7 @@ STB_API int stb_resample_mono(const void* pcm, int sample_format, int channels, 
  *    GreedyDecoder.update).  One step = one decoder forward for the newest token of B sequences.
  *    Everything position-dependent is read from the DEVICE counter `pos` (index of the token being fed), which the step
  *    increments at its end, so a single captured CUDA graph can replay every step.
- *    state: self-attention K/V caches fp16 [L][2][B][n_text_ctx][d] (stb_decode_state_bytes).
+ *    state: self-attention K/V caches fp32 [L][2][B][n_text_ctx][d] (stb_decode_state_bytes).
  *    tokens_in [B] int32 -> logits_out [B][ld_logits] fp32. */
 STB_API size_t stb_decode_state_bytes(const stb_model* m, int B);
 STB_API size_t stb_decode_ws_bytes(const stb_model* m, int B);

@@ -438,7 +438,7 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     return w;
 }
 static size_t decode_state_bytes(const stb_model* m, int B, int cache_rows) {
-    return (size_t)m->dims.n_text_layer * 2 * B * cache_rows * m->dims.n_text_state * sizeof(__half);
+    return (size_t)m->dims.n_text_layer * 2 * B * cache_rows * m->dims.n_text_state * sizeof(float);
 }
 
 // seq_off (nullable) [B]: first cache row of each sequence; cache_rows: rows per sequence of the K/V caches (>= n_text_ctx
@@ -537,8 +537,8 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
         const bool last = l + 1 == D.n_text_layer;
         const float* next_g = last ? final_g : W_F32(m->dec[l + 1], STB_L_ATTN_LN_G);
         const float* next_b = last ? final_b : W_F32(m->dec[l + 1], STB_L_ATTN_LN_B);
-        __half* Kc = (__half*)state + (size_t)l * 2 * cache;
-        __half* Vc = Kc + cache;
+        float* Kc = (float*)state + (size_t)l * 2 * cache;
+        float* Vc = Kc + cache;
         // w.ln holds attn_ln(x) here (previous layer's fc2 finish, or the standalone LayerNorm above)
         STB_TRY(lin(w.ln, d, W_HI(L, STB_L_QKV_W), W_LO(L, STB_L_QKV_W), 3 * d, W_F32(L, STB_L_QKV_B), STB_ACT_NONE, nullptr,
                     w.qkv, none, 3 * d, nullptr, nullptr));

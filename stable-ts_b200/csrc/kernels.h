@@ -36,7 +36,7 @@ int capture_heads(const float* S, int B, int H, int M, long long ld, float* out,
                   cudaStream_t st);
 
 // seq_off (nullable) [B]: first cache row of each sequence (ragged initial tokens right-aligned on the shared counter)
-int decode_attn_self(const float* qkv, __half* Kc, __half* Vc, int B, int H, int d, int ctx, const int32_t* pos,
+int decode_attn_self(const float* qkv, float* Kc, float* Vc, int B, int H, int d, int ctx, const int32_t* pos,
                      const int32_t* seq_off, __half* oh, __half* ol, float* of, cudaStream_t st);
 // decode-step view of one layer's cross K / V: fp16 planes, head-major [B][H][T][64] (K is the GEMM hi plane itself)
 struct CrossDecodeKV {

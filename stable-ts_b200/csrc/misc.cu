@@ -67,7 +67,7 @@ static const OptDef g_opt_defs[OPT_COUNT] = {
     // half-batches are stepped concurrently on two streams)
     {"decode_lin_priority", "STB_DECODE_LIN_PRIORITY", 1},
     // 1: decode-step cross-attention on the warp-level tensor cores (ldmatrix + mma.sync over TMA-swizzled K / V tiles)
-    {"xattn_tc", "STB_XATTN_TC", 0},
+    {"xattn_tc", "STB_XATTN_TC", 1},
 };
 static int g_opt[OPT_COUNT];
 static bool g_opt_init = false;

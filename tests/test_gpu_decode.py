@@ -240,6 +240,7 @@ def test_cross_attention_tensor_core_variant():
     audios[2, 200000:] = 0                                    # a window whose tail is silence
     opt = DecodingOptions(sample_len=6)
     V = dims.n_vocab
+    default = L.get_option("xattn_tc")
     try:
         for rep in (1, 14):                                   # B = 3 (GEMV path) and B = 42 (cluster linears)
             enc = gm.encode(gm.log_mel(audios.repeat(rep, 1).cuda()))
@@ -267,4 +268,4 @@ def test_cross_attention_tensor_core_variant():
         res, _ = decode_windows(gm2, tk2, gm2.encode(gm2.log_mel(audio.cuda()[None])), DecodingOptions(language="en", sample_len=16))
         assert res[0].tokens == ref.tokens and abs(res[0].avg_logprob - ref.avg_logprob) < 1e-3
     finally:
-        L.set_option("xattn_tc", 0)
+        L.set_option("xattn_tc", default)
