@@ -246,21 +246,23 @@ def test_cross_attention_tensor_core_variant():
             enc = gm.encode(gm.log_mel(audios.repeat(rep, 1).cuda()))
             L.set_option("xattn_tc", 0)
             r0, x0 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
-            L.set_option("xattn_tc", 1)
-            r1, x1 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
-            worst = 0.0
-            for a, b in zip(x0["step_logits"], x1["step_logits"]):
-                a, b = a.float().cpu(), b.float().cpu()
-                fin = a > -1e30
-                assert torch.equal(fin, b > -1e30)
-                worst = max(worst, ((a[fin] - b[fin]).abs().max() / a[fin].abs().max()).item())
-            print(f"B={3 * rep}: tensor-core vs scalar cross-attention, worst step-logit rel diff {worst:.2e}")
-            assert worst < 2e-5
-            for a, b in zip(r0, r1):
-                assert a.tokens == b.tokens
-            rg, _ = decode_windows(gm, tk, enc, opt)          # graph replay with the option on
-            for a, b in zip(r0, rg):
-                assert a.tokens == b.tokens
+            for variant in (1, 2):                            # 1: one item per CTA, 2: persistent, double-buffered
+                L.set_option("xattn_tc", variant)
+                r1, x1 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
+                worst = 0.0
+                for a, b in zip(x0["step_logits"], x1["step_logits"]):
+                    a, b = a.float().cpu(), b.float().cpu()
+                    fin = a > -1e30
+                    assert torch.equal(fin, b > -1e30)
+                    worst = max(worst, ((a[fin] - b[fin]).abs().max() / a[fin].abs().max()).item())
+                print(f"B={3 * rep}: tensor-core variant {variant} vs scalar cross-attention, worst step-logit rel diff {worst:.2e}")
+                assert worst < 2e-5
+                for a, b in zip(r0, r1):
+                    assert a.tokens == b.tokens
+                rg, _ = decode_windows(gm, tk, enc, opt)      # graph replay with the option on
+                for a, b in zip(r0, rg):
+                    assert a.tokens == b.tokens
+            L.set_option("xattn_tc", default)
         # against the CPU oracle (tiny.en, free-running greedy)
         W2, om, gm2, tk2 = _mk("tiny.en", 3)
         audio = SP.synth_audio(480000, seed=7)
