@@ -589,8 +589,10 @@ def run_b200(args, dims_tuple):
         if xp and xp["ms"] > 0 and xp["n"] > 0:
             x_gbs = xp["bytes"] / (xp["ms"] * 1e-3) / 1e9
             H = model.dims.n_text_head
-            traffic, traffic_src = ncu_traffic("decode_cross_attn_kernel", xp["bytes"] / xp["n"])
-            roof_x = {"bound": "hbm", "kernel": "decode_cross_attn_kernel (flash-decoding over the per-window cross K/V)",
+            variant = {0: "decode_cross_attn_kernel (scalar lanes)", 1: "decode_cross_attn_tc_kernel (ldmatrix + mma.sync)"}.get(
+                L.get_option("xattn_tc"), "decode_cross_attn")
+            traffic, traffic_src = ncu_traffic(variant.split(" ")[0], xp["bytes"] / xp["n"])
+            roof_x = {"bound": "hbm", "kernel": variant + ": flash-decoding over the per-window cross K/V, TMA-fed",
                       "achieved": x_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": x_gbs / hbm_peak,
                       "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                       "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": xp["bytes"] / xp["n"],

@@ -43,9 +43,11 @@ extern "C" {
 
 STB_API const char* stb_last_error(void);
 STB_API int stb_abi_version(void);
-/* run-time switches for A/B measurement of kernel variants on the same box: "decode_splitk_legacy" (0/1: decode-step linears
- * as swapped split-K GEMM + finish kernel instead of the cluster kernel); unknown names are an error.  Not part of the
- * reference's behaviour -- every setting must pass the same parity tests. */
+/* run-time switches for A/B measurement of kernel variants on the same box (defaults also from the environment: STB_<NAME>):
+ *   "decode_splitk_legacy" 0/1  decode-step linears as swapped split-K GEMM + finish kernel instead of the cluster kernel;
+ *   "xattn_tc"             1/0  decode-step cross-attention on ldmatrix + mma.sync over TMA-swizzled tiles / on scalar lanes;
+ *   "decode_lin_priority"  1/0  greatest launch priority for the decode-step linears (matters with concurrent chains only).
+ * Unknown names are an error.  Not part of the reference's behaviour -- every setting must pass the same parity tests. */
 STB_API int stb_set_option(const char* name, int value);
 STB_API int stb_get_option(const char* name);
 /* measurement hooks (bench.py): kernels launched by this library so far; per-launch CUDA-event timing of every kernel */

@@ -308,6 +308,9 @@ decode_cross_attn_kernel(const float* __restrict__ q, const __half* __restrict__
 //   * one exact softmax per CTA (max over its 192 keys through shared memory; partials of the 8 splits are merged as before);
 //   * P.V: mma.sync m16n8k8 per 8-key tile, A = p in rows 0 / 1 (hi / lo), B = V through ldmatrix.trans.
 // Warp w owns tiles w, w + 4, w + 8 of each 12-tile chunk.
+// (A persistent, double-buffered form of this kernel -- 2 CTAs per SM walking the items, the next item's copies in flight
+//  during the reduction -- was measured at 382 vs 166 us per launch, like its scalar predecessor in round 2's first call: the
+//  per-item fence + ticket + barriers serialise inside a CTA, whereas 4 short-lived CTAs per SM overlap each other's tails.)
 // ---------------------------------------------------------------------------------------------------------
 constexpr int XT_KEYS = 96;                  // keys per chunk
 constexpr int XT_CHUNKS = 2;                 // chunks per split: 8 x 192 = 1536 >= 1500
@@ -504,197 +507,6 @@ decode_cross_attn_tc_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
             out_hi[oo] = hi;
             if (out_lo) out_lo[oo] = lo;
         }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// PERSISTENT form of the tensor-core kernel (option "xattn_tc" = 2): 2 CTAs per SM walk the (sequence, head, split) items
-// with a double-buffered tile, so the TMA copies of item i + 1 are in flight while item i is reduced.  The one-item kernel
-// above loads 48 KB and then computes with nothing in flight; its 4 CTAs per SM start together and stay in phase, which is
-// where the last ~15 % of the HBM roofline go (measured 0.84).  Same arithmetic, same partial / ticket protocol.
-// ---------------------------------------------------------------------------------------------------------
-constexpr int XP_BUF = XT_CHUNKS * 2 * XT_KEYS * 128;       // one item: K | V of both chunks, 49152 B
-constexpr int XP_SMEM = 2 * XP_BUF + 1024;
-
-__global__ void __launch_bounds__(128, 2)
-decode_cross_attn_tc_persist_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                                    const XPerm perm, const float* __restrict__ q, int d, int T, int H, int n_items,
-                                    float* __restrict__ partial, int* __restrict__ tickets, __half* __restrict__ out_hi,
-                                    __half* __restrict__ out_lo, float* __restrict__ out_f32) {
-    extern __shared__ uint8_t xt_dyn[];
-    uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xt_dyn) + 1023) & ~uintptr_t(1023));
-    __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ float s_m[4], s_l[4];
-    __shared__ float s_acc[4][64];
-    __shared__ int s_last;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int mrow = lane & 7, mat = lane >> 3;
-    const int stride = gridDim.x;
-    const int n_my = (n_items - (int)blockIdx.x + stride - 1) / stride;
-
-    auto issue = [&](int it) {                               // thread 0: both chunks of item `it` into buffer it & 1
-        const int item = blockIdx.x + it * stride;
-        const int split = item % XS, bh = item / XS, h = bh % H, b = bh / H;
-        uint8_t* dst = sm + (size_t)(it & 1) * XP_BUF;
-        mbar_arrive_expect_tx(&s_bar[it & 1], (uint32_t)XP_BUF);
-#pragma unroll
-        for (int c = 0; c < XT_CHUNKS; ++c) {
-            int v[4] = {split * (XT_CHUNKS * XT_KEYS) + c * XT_KEYS, h, b, 0};
-            tma_load_4d(dst + (size_t)c * 2 * XT_KEYS * 128, &tmK, &s_bar[it & 1], 0, v[perm.p[0]], v[perm.p[1]], v[perm.p[2]]);
-            tma_load_4d(dst + (size_t)c * 2 * XT_KEYS * 128 + XT_KEYS * 128, &tmV, &s_bar[it & 1], 0, v[perm.p[0]], v[perm.p[1]],
-                        v[perm.p[2]]);
-        }
-    };
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmK);
-        tma_prefetch_desc(&tmV);
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (n_my > 0) issue(0);
-        if (n_my > 1) issue(1);
-    }
-    pdl_trigger();
-    pdl_wait();                                              // q comes from the preceding linear
-    for (int it = 0; it < n_my; ++it) {
-        const int item = blockIdx.x + it * stride;
-        const int split = item % XS, bh = item / XS, h = bh % H, b = bh / H;
-        const int key0 = split * (XT_CHUNKS * XT_KEYS);
-        uint32_t qa0[4], qa2[4];
-        {
-            const float* qp = q + (long long)b * d + h * 64;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                __half hv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int idx = ks * 16 + 2 * t + (e & 1) + (e >> 1) * 8;
-                    const float x = __ldg(qp + idx) * (0.125f * LOG2E_F);
-                    __half hi, lo;
-                    split_f16(x, hi, lo);
-                    hv[e] = g == 0 ? hi : (g == 1 ? lo : __float2half(0.f));
-                }
-                qa0[ks] = pack_h2(hv[0], hv[1]);
-                qa2[ks] = pack_h2(hv[2], hv[3]);
-            }
-        }
-        const uint32_t buf = smem_u32(sm) + (uint32_t)((it & 1) * XP_BUF);
-        mbar_wait(&s_bar[it & 1], (uint32_t)((it >> 1) & 1), 44);
-        float sc[XT_CHUNKS * XT_TILES][2];
-#pragma unroll
-        for (int c = 0; c < XT_CHUNKS; ++c) {
-            const uint32_t kbase = buf + (uint32_t)(c * 2 * XT_KEYS * 128);
-#pragma unroll
-            for (int i = 0; i < XT_TILES; ++i) {
-                const int r0 = (w + 4 * i) * 8;
-                const int row = r0 + mrow;
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[4];
-                    ldsm_x4(r, kbase + (uint32_t)(row * 128) + (uint32_t)((((half * 4 + mat) ^ (row & 7)) << 4)));
-                    mma_16816(acc, qa0[half * 2], qa2[half * 2], r[0], r[1]);
-                    mma_16816(acc, qa0[half * 2 + 1], qa2[half * 2 + 1], r[2], r[3]);
-                }
-                const float s0 = acc[0] + __shfl_down_sync(0xffffffffu, acc[0], 4);
-                const float s1 = acc[1] + __shfl_down_sync(0xffffffffu, acc[1], 4);
-                const int key = key0 + c * XT_KEYS + r0 + 2 * t;
-                sc[c * XT_TILES + i][0] = (g == 0 && key < T) ? s0 : -INFINITY;
-                sc[c * XT_TILES + i][1] = (g == 0 && key + 1 < T) ? s1 : -INFINITY;
-            }
-        }
-        float m = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < XT_CHUNKS * XT_TILES; ++i) m = fmaxf(m, fmaxf(sc[i][0], sc[i][1]));
-        m = warp_max(m);
-        if (lane == 0) s_m[w] = m;
-        __syncthreads();
-        const float M = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
-        float l = 0.f;
-        float oacc[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) { oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f; }
-#pragma unroll
-        for (int c = 0; c < XT_CHUNKS; ++c) {
-            const uint32_t vbase = buf + (uint32_t)(c * 2 * XT_KEYS * 128 + XT_KEYS * 128);
-#pragma unroll
-            for (int i = 0; i < XT_TILES; ++i) {
-                const float p0 = (M == -INFINITY) ? 0.f : exp2f(sc[c * XT_TILES + i][0] - M);
-                const float p1 = (M == -INFINITY) ? 0.f : exp2f(sc[c * XT_TILES + i][1] - M);
-                l += p0 + p1;
-                __half h0, l0, h1, l1;
-                split_f16(p0, h0, l0);
-                split_f16(p1, h1, l1);
-                const uint32_t hi = pack_h2(h0, h1), lo = pack_h2(l0, l1);
-                const uint32_t lo_up = __shfl_up_sync(0xffffffffu, lo, 4);
-                const uint32_t a0 = g == 0 ? hi : (g == 1 ? lo_up : 0u);
-                const int r0 = (w + 4 * i) * 8;
-                const int row = r0 + mrow;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[4];
-                    ldsm_x4_t(r, vbase + (uint32_t)(row * 128) + (uint32_t)((((half * 4 + mat) ^ (row & 7)) << 4)));
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) mma_1688(oacc[half * 4 + j], a0, r[j]);
-                }
-            }
-        }
-        l = warp_sum(l);
-        if (lane == 0) s_l[w] = l;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const float o0 = oacc[nt][0] + __shfl_down_sync(0xffffffffu, oacc[nt][0], 4);
-            const float o1 = oacc[nt][1] + __shfl_down_sync(0xffffffffu, oacc[nt][1], 4);
-            if (g == 0) {
-                s_acc[w][nt * 8 + 2 * t] = o0;
-                s_acc[w][nt * 8 + 2 * t + 1] = o1;
-            }
-        }
-        __syncthreads();                                     // every warp is done with the tile: it can be refilled
-        if (threadIdx.x == 0 && it + 2 < n_my) issue(it + 2);
-        float* part = partial + (long long)item * 66;
-        if (threadIdx.x < 64) {
-            part[2 + threadIdx.x] = (s_acc[0][threadIdx.x] + s_acc[1][threadIdx.x]) + (s_acc[2][threadIdx.x] + s_acc[3][threadIdx.x]);
-            if (threadIdx.x == 0) { part[0] = M; part[1] = (s_l[0] + s_l[1]) + (s_l[2] + s_l[3]); }
-            __threadfence();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const int tk = atomicAdd(tickets + bh, 1);
-            s_last = (tk == XS - 1);
-            if (s_last) tickets[bh] = 0;                     // re-arm for the next launch
-        }
-        __syncthreads();
-        if (s_last && threadIdx.x < 64) {
-            __threadfence();
-            const float* p0 = partial + (long long)bh * XS * 66;
-            float Mx = -INFINITY;
-#pragma unroll
-            for (int i = 0; i < XS; ++i) Mx = fmaxf(Mx, __ldcg(p0 + i * 66));
-            float Lsum = 0.f, o = 0.f;
-#pragma unroll
-            for (int i = 0; i < XS; ++i) {
-                const float mi = __ldcg(p0 + i * 66);
-                const float scl = (mi == -INFINITY) ? 0.f : exp2f(mi - Mx);
-                Lsum += __ldcg(p0 + i * 66 + 1) * scl;
-                o += __ldcg(p0 + i * 66 + 2 + threadIdx.x) * scl;
-            }
-            o /= Lsum;
-            const long long oo = (long long)b * d + h * 64 + threadIdx.x;
-            if (out_f32) out_f32[oo] = o;
-            if (out_hi) {
-                __half hi, lo;
-                split_f16(o, hi, lo);
-                out_hi[oo] = hi;
-                if (out_lo) out_lo[oo] = lo;
-            }
-        }
-        __syncthreads();                                     // s_m / s_l / s_acc / s_last are reused by the next item
     }
 }
 
@@ -985,20 +797,6 @@ int decode_attn_cross(const float* q, const CrossDecodeKV& kv, int B, int H, int
         for (int i = 0; i < 3; ++i) {
             STB_REQUIRE(tk.perm[i] == tv.perm[i], "decode_attn_cross: K / V tensor maps disagree");
             perm.p[i] = tk.perm[i];
-        }
-        if (option(OPT_XATTN_TC) == 2) {
-            static bool attr_p[64] = {};
-            if (dev >= 0 && dev < 64 && !attr_p[dev]) {
-                STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, XP_SMEM));
-                STB_CUDA_OK(cudaFuncSetAttribute(decode_cross_attn_tc_persist_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-                attr_p[dev] = true;
-            }
-            const int n_items = B * H * XS;
-            const int grid = n_items < 2 * sm_count() ? n_items : 2 * sm_count();
-            STB_CUDA_OK(launch_pdl(decode_cross_attn_tc_persist_kernel, dim3(grid), dim3(128), (size_t)XP_SMEM, st, tk.map, tv.map, perm,
-                                   q, d, T, H, n_items, partial, tickets, oh, ol, of));
-            STB_LAUNCH_OK();
-            return STB_OK;
         }
         STB_CUDA_OK(launch_pdl(decode_cross_attn_tc_kernel, dim3(XS, H, B), dim3(128), (size_t)XT_SMEM, st, tk.map, tv.map, perm, q, d,
                                T, partial, tickets, oh, ol, of));

@@ -246,7 +246,7 @@ def test_cross_attention_tensor_core_variant():
             enc = gm.encode(gm.log_mel(audios.repeat(rep, 1).cuda()))
             L.set_option("xattn_tc", 0)
             r0, x0 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
-            for variant in (1, 2):                            # 1: one item per CTA, 2: persistent, double-buffered
+            for variant in (1,):
                 L.set_option("xattn_tc", variant)
                 r1, x1 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
                 worst = 0.0
