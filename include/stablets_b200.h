@@ -46,7 +46,8 @@ STB_API int stb_abi_version(void);
 /* run-time switches for A/B measurement of kernel variants on the same box (defaults also from the environment: STB_<NAME>):
  *   "decode_splitk_legacy" 0/1  decode-step linears as swapped split-K GEMM + finish kernel instead of the cluster kernel;
  *   "xattn_tc"             1/0  decode-step cross-attention on ldmatrix + mma.sync over TMA-swizzled tiles / on scalar lanes;
- *   "decode_lin_priority"  1/0  greatest launch priority for the decode-step linears (matters with concurrent chains only).
+ *   "decode_lin_priority"  1/0  greatest launch priority for the decode-step linears (matters with concurrent chains only);
+ *   "decode_fused_ln"      0/1  LayerNorm folded into the decode-step linears (needs the STB_L_*_WG / *_FOLD tensors).
  * Unknown names are an error.  Not part of the reference's behaviour -- every setting must pass the same parity tests. */
 STB_API int stb_set_option(const char* name, int value);
 STB_API int stb_get_option(const char* name);
@@ -153,12 +154,21 @@ enum {
     STB_T_DEC_POS,         /* f32 [n_text_ctx][d] */
     STB_T_DEC_LN_G,
     STB_T_DEC_LN_B,
+    /* optional, decode step with the final LayerNorm folded into the vocabulary projection (see STB_L_*_WG below) */
+    STB_T_DEC_TOKEMB_G,    /* split [V][d]: token embedding * ln.weight (column-wise) */
+    STB_T_DEC_TOKEMB_FOLD, /* f32 [2][V]: row sums of the split planes | emb . ln.bias */
     STB_T_LAYER_BASE = 32,
     /* per-layer ids (add to STB_T_LAYER_BASE); encoder layers use ENC_*, decoder layers DEC_* */
     STB_L_ATTN_LN_G = 0, STB_L_ATTN_LN_B, STB_L_QKV_W /* split [3d][d]: q,k,v */, STB_L_QKV_B /* f32 [3d], k part 0 */,
     STB_L_OUT_W, STB_L_OUT_B, STB_L_MLP_LN_G, STB_L_MLP_LN_B, STB_L_FC1_W, STB_L_FC1_B, STB_L_FC2_W, STB_L_FC2_B,
     STB_L_CROSS_LN_G, STB_L_CROSS_LN_B, STB_L_CQ_W, STB_L_CQ_B, STB_L_CKV_W /* split [2d][d]: k,v */,
     STB_L_CKV_B /* f32 [2d], k part 0 */, STB_L_COUT_W, STB_L_COUT_B,
+    /* OPTIONAL (decoder layers): the LayerNorm in front of a decode-step Linear folded into it.  With W' = W diag(g),
+     * y = rstd (W' x - mean * rowsum(W')) + (W beta + bias): the step's GEMM runs on the raw residual stream x, its epilogue
+     * applies the row statistics that the PRODUCER of x left behind -- no LayerNorm launch (3 per layer) in the step.
+     *   *_WG    split [n][d]   W' (hi / lo planes)
+     *   *_FOLD  f32 [2][n]     rowsum of the planes (what the tensor core multiplies) | W beta + bias */
+    STB_L_QKV_WG, STB_L_QKV_FOLD, STB_L_CQ_WG, STB_L_CQ_FOLD, STB_L_FC1_WG, STB_L_FC1_FOLD,
     STB_L_COUNT
 };
 

@@ -16,10 +16,11 @@ N_FRAMES, N_AUDIO_CTX, KPAD = 3000, 1500, 1504
 
 # tensor ids (include/stablets_b200.h)
 (T_ENC_CONV1_W, T_ENC_CONV1_B, T_ENC_CONV2_W, T_ENC_CONV2_B, T_ENC_POS, T_ENC_LNPOST_G, T_ENC_LNPOST_B,
- T_DEC_TOKEMB_F32, T_DEC_TOKEMB, T_DEC_POS, T_DEC_LN_G, T_DEC_LN_B) = range(12)
+ T_DEC_TOKEMB_F32, T_DEC_TOKEMB, T_DEC_POS, T_DEC_LN_G, T_DEC_LN_B, T_DEC_TOKEMB_G, T_DEC_TOKEMB_FOLD) = range(14)
 T_LAYER_BASE = 32
 (L_ATTN_LN_G, L_ATTN_LN_B, L_QKV_W, L_QKV_B, L_OUT_W, L_OUT_B, L_MLP_LN_G, L_MLP_LN_B, L_FC1_W, L_FC1_B, L_FC2_W,
- L_FC2_B, L_CROSS_LN_G, L_CROSS_LN_B, L_CQ_W, L_CQ_B, L_CKV_W, L_CKV_B, L_COUT_W, L_COUT_B, L_COUNT) = range(21)
+ L_FC2_B, L_CROSS_LN_G, L_CROSS_LN_B, L_CQ_W, L_CQ_B, L_CKV_W, L_CKV_B, L_COUT_W, L_COUT_B, L_QKV_WG, L_QKV_FOLD, L_CQ_WG,
+ L_CQ_FOLD, L_FC1_WG, L_FC1_FOLD, L_COUNT) = range(27)
 
 
 class Operand(ctypes.Structure):

@@ -33,6 +33,15 @@ struct DLArgs {
     __half* out_hi;
     __half* out_lo;
     long long ld_out;
+    // LayerNorm folded into this Linear (DLFuse): out = rstd_s (acc - mean_s wsum[n]) + bias[n], the row statistics of
+    // sequence s summed from ln_tiles partial (sum, sum of squares) pairs [ln_tiles][B][2] left by the producer of x
+    const float* ln_stats;
+    int ln_tiles;
+    float ln_dinv;            // 1 / (features of the normalised row)
+    const float* ln_wsum;     // [n]
+    // this Linear produces a row that the NEXT Linear normalises: per 128-feature tile the (sum, sum of squares) of the
+    // final values (after bias / activation / residual) of every sequence, [tiles][B][2]
+    float* stats_out;
 };
 
 __device__ __forceinline__ uint32_t cluster_rank() {
@@ -226,9 +235,11 @@ decode_linear_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_cons
     __syncwarp();
     cluster_sync_all();                                         // every peer's tile is complete and visible
     if (warp >= 2) {
-        // Reduce-scatter over distributed shared memory: rank r owns sequences [r BN / split, (r + 1) BN / split).  A thread
-        // handles 4 consecutive features of one sequence: it issues the 16-byte loads of ALL peers first (independent, so their
-        // DSMEM latencies overlap), adds them in rank order (bit-reproducible), applies the epilogue and stores 16 bytes.
+        // Reduce-scatter over distributed shared memory: rank r owns sequences [r BN / split, (r + 1) BN / split).  A warp
+        // handles one sequence per iteration, a lane 4 consecutive features of it: it issues the 16-byte loads of ALL peers
+        // first (independent, so their DSMEM latencies overlap), adds them in rank order (bit-reproducible), applies the
+        // epilogue and stores 16 bytes.  Every lane walks the loop (warp-uniform bounds): the folded LayerNorm and the row
+        // statistics below are warp reductions.
         const int e = (warp - 2) * 32 + lane;                  // 0 .. 127
         const int quad = e & 31;                               // features m0 + 4 quad .. + 3
         const int m = m0 + quad * 4;
@@ -237,58 +248,92 @@ decode_linear_kernel(const __grid_constant__ CUtensorMap tmWh, const __grid_cons
         uint32_t peer[8];
 #pragma unroll
         for (int p = 0; p < 8; ++p) peer[p] = p < split ? dsmem_addr(local, (uint32_t)p) : 0u;
-        pdl_wait();                                             // the residual is an earlier kernel's output
-        const bool vec = m + 3 < g.n && (g.ld_out & 3) == 0 && (g.res == nullptr || (g.ld_res & 3) == 0);
-        float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (g.bias != nullptr) {
-            if (m + 3 < g.n) bias = __ldg(reinterpret_cast<const float4*>(g.bias + m));
-            else {
-                if (m < g.n) bias.x = __ldg(g.bias + m);
-                if (m + 1 < g.n) bias.y = __ldg(g.bias + m + 1);
-                if (m + 2 < g.n) bias.z = __ldg(g.bias + m + 2);
+        pdl_wait();                                             // residual and row statistics are earlier kernels' outputs
+        const bool full = m + 3 < g.n;                          // all 4 features exist
+        const bool vec = full && (g.ld_out & 3) == 0 && (g.res == nullptr || (g.ld_res & 3) == 0);
+        auto load4 = [&](const float* p) -> float4 {            // 4 per-feature constants, zero past n
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p == nullptr) return r;
+            if (full) return __ldg(reinterpret_cast<const float4*>(p + m));
+            if (m < g.n) r.x = __ldg(p + m);
+            if (m + 1 < g.n) r.y = __ldg(p + m + 1);
+            if (m + 2 < g.n) r.z = __ldg(p + m + 2);
+            return r;
+        };
+        const float4 bias = load4(g.bias);
+        const float4 wsum = load4(g.ln_wsum);
+        const int tile = blockIdx.x / split;
+        for (int c = c0 + (e >> 5); c < c1 && c < g.B; c += 4) {
+            const uint32_t off = (uint32_t)((c * 128 + quad * 4) * 4);
+            float4 v[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p)
+                if (p < split) v[p] = dsmem_ld4(peer[p] + off);
+            float4 a = v[0];
+#pragma unroll
+            for (int p = 1; p < 8; ++p)
+                if (p < split) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
+            if (g.ln_stats != nullptr) {                        // folded LayerNorm of the input row of sequence c
+                float s1 = 0.f, s2 = 0.f;
+                if (quad < g.ln_tiles) {
+                    const float2 pr = *reinterpret_cast<const float2*>(g.ln_stats + ((long long)quad * g.B + c) * 2);
+                    s1 = pr.x;
+                    s2 = pr.y;
+                }
+                s1 = warp_sum(s1);                              // fixed shuffle tree: reproducible
+                s2 = warp_sum(s2);
+                const double mu = (double)s1 * (double)g.ln_dinv;
+                const double var = (double)s2 * (double)g.ln_dinv - mu * mu;
+                const float rstd = (float)(1.0 / sqrt(var + 1e-5));
+                const float muf = (float)mu;
+                a.x = (a.x - muf * wsum.x) * rstd; a.y = (a.y - muf * wsum.y) * rstd;
+                a.z = (a.z - muf * wsum.z) * rstd; a.w = (a.w - muf * wsum.w) * rstd;
             }
-        }
-        if (m < g.n) {
-            for (int c = c0 + (e >> 5); c < c1 && c < g.B; c += 4) {
-                const uint32_t off = (uint32_t)((c * 128 + quad * 4) * 4);
-                float4 v[8];
-#pragma unroll
-                for (int p = 0; p < 8; ++p)
-                    if (p < split) v[p] = dsmem_ld4(peer[p] + off);
-                float4 a = v[0];
-#pragma unroll
-                for (int p = 1; p < 8; ++p)
-                    if (p < split) { a.x += v[p].x; a.y += v[p].y; a.z += v[p].z; a.w += v[p].w; }
-                a.x += bias.x; a.y += bias.y; a.z += bias.z; a.w += bias.w;
-                if (g.act == STB_ACT_GELU) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
-                const long long off_o = (long long)c * g.ld_out + m;
+            a.x += bias.x; a.y += bias.y; a.z += bias.z; a.w += bias.w;
+            if (g.act == STB_ACT_GELU) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+            if (g.res != nullptr) {
+                const float* rp = g.res + (long long)c * g.ld_res + m;
                 if (vec) {
-                    if (g.res != nullptr) {
-                        const float4 r = *reinterpret_cast<const float4*>(g.res + (long long)c * g.ld_res + m);
-                        a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
-                    }
-                    if (g.out_f32 != nullptr) *reinterpret_cast<float4*>(g.out_f32 + off_o) = a;
-                    if (g.out_hi != nullptr) {
-                        __half h[4], l[4];
-                        split_f16(a.x, h[0], l[0]); split_f16(a.y, h[1], l[1]);
-                        split_f16(a.z, h[2], l[2]); split_f16(a.w, h[3], l[3]);
-                        *reinterpret_cast<uint2*>(g.out_hi + off_o) = *reinterpret_cast<const uint2*>(h);
-                        if (g.out_lo != nullptr) *reinterpret_cast<uint2*>(g.out_lo + off_o) = *reinterpret_cast<const uint2*>(l);
-                    }
+                    const float4 r = *reinterpret_cast<const float4*>(rp);
+                    a.x += r.x; a.y += r.y; a.z += r.z; a.w += r.w;
                 } else {
-                    const float vals[4] = {a.x, a.y, a.z, a.w};
+                    if (m < g.n) a.x += rp[0];
+                    if (m + 1 < g.n) a.y += rp[1];
+                    if (m + 2 < g.n) a.z += rp[2];
+                    if (m + 3 < g.n) a.w += rp[3];
+                }
+            }
+            if (g.stats_out != nullptr) {                       // partial row statistics of this 128-feature tile
+                float s1 = 0.f, s2 = 0.f;
+                if (m < g.n) { s1 += a.x; s2 += a.x * a.x; }
+                if (m + 1 < g.n) { s1 += a.y; s2 += a.y * a.y; }
+                if (m + 2 < g.n) { s1 += a.z; s2 += a.z * a.z; }
+                if (m + 3 < g.n) { s1 += a.w; s2 += a.w * a.w; }
+                s1 = warp_sum(s1);
+                s2 = warp_sum(s2);
+                if (quad == 0) *reinterpret_cast<float2*>(g.stats_out + ((long long)tile * g.B + c) * 2) = make_float2(s1, s2);
+            }
+            const long long off_o = (long long)c * g.ld_out + m;
+            if (vec) {
+                if (g.out_f32 != nullptr) *reinterpret_cast<float4*>(g.out_f32 + off_o) = a;
+                if (g.out_hi != nullptr) {
+                    __half h[4], l[4];
+                    split_f16(a.x, h[0], l[0]); split_f16(a.y, h[1], l[1]);
+                    split_f16(a.z, h[2], l[2]); split_f16(a.w, h[3], l[3]);
+                    *reinterpret_cast<uint2*>(g.out_hi + off_o) = *reinterpret_cast<const uint2*>(h);
+                    if (g.out_lo != nullptr) *reinterpret_cast<uint2*>(g.out_lo + off_o) = *reinterpret_cast<const uint2*>(l);
+                }
+            } else {
+                const float vals[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (m + j >= g.n) break;
-                        float x = vals[j];
-                        if (g.res != nullptr) x += g.res[(long long)c * g.ld_res + m + j];
-                        if (g.out_f32 != nullptr) g.out_f32[off_o + j] = x;
-                        if (g.out_hi != nullptr) {
-                            __half hi, lo;
-                            split_f16(x, hi, lo);
-                            g.out_hi[off_o + j] = hi;
-                            if (g.out_lo != nullptr) g.out_lo[off_o + j] = lo;
-                        }
+                for (int j = 0; j < 4; ++j) {
+                    if (m + j >= g.n) break;
+                    if (g.out_f32 != nullptr) g.out_f32[off_o + j] = vals[j];
+                    if (g.out_hi != nullptr) {
+                        __half hi, lo;
+                        split_f16(vals[j], hi, lo);
+                        g.out_hi[off_o + j] = hi;
+                        if (g.out_lo != nullptr) g.out_lo[off_o + j] = lo;
                     }
                 }
             }
@@ -366,7 +411,7 @@ static int launch_dl(const TmapVal& wh, const TmapVal& wl, const TmapVal& xh, co
 // out[B][n] = epilogue(x[B][k] . W[n][k]^T); x / W split-fp16 planes, K-major; B <= 128; k a multiple of 64.
 int decode_linear(const void* x_hi, const void* x_lo, int B, int k, const void* w_hi, const void* w_lo, int n, const float* bias,
                   int act, const float* res, long long ld_res, float* out_f32, void* out_hi, void* out_lo, long long ld_out,
-                  cudaStream_t st) {
+                  const DLFuse* fuse, cudaStream_t st) {
     STB_REQUIRE(x_hi && w_hi && (out_f32 || out_hi), "decode_linear: null argument");
     STB_REQUIRE(B >= 1 && B <= 128 && k % 64 == 0 && n >= 1, "decode_linear: unsupported shape B=%d k=%d n=%d", B, k, n);
     STB_REQUIRE((x_lo != nullptr) == (w_lo != nullptr), "decode_linear: lo planes must be given for both operands or neither");
@@ -376,6 +421,15 @@ int decode_linear(const void* x_hi, const void* x_lo, int B, int k, const void* 
     g.n = n; g.B = B; g.kb_total = k / 64;
     g.bias = bias; g.act = act; g.res = res; g.ld_res = ld_res;
     g.out_f32 = out_f32; g.out_hi = (__half*)out_hi; g.out_lo = (__half*)out_lo; g.ld_out = ld_out;
+    if (fuse != nullptr) {
+        if (fuse->stats_in != nullptr) {
+            STB_REQUIRE(fuse->wsum != nullptr && fuse->tiles_in >= 1 && fuse->tiles_in <= 32 && fuse->row_features >= 1,
+                        "decode_linear: folded LayerNorm needs wsum and 1..32 statistic tiles");
+            g.ln_stats = fuse->stats_in; g.ln_tiles = fuse->tiles_in; g.ln_dinv = 1.0f / (float)fuse->row_features;
+            g.ln_wsum = fuse->wsum;
+        }
+        g.stats_out = fuse->stats_out;
+    }
     const int split = decode_linear_split(n, k);
     TmapVal wh, wl, xh, xl;
     STB_TRY(make_tmap(w_hi, n, k, 1, 1, k, 0, 0, 128, &wh));

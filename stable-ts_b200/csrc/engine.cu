@@ -403,6 +403,8 @@ struct StepWs {
     float* xpart;      // cross-attention split partials + tickets
     int* tickets;
     Split ln, attn, hid;
+    Split xs;          // split planes of the raw residual stream x (LayerNorm folded into the consumer, OPT_DECODE_FUSED_LN)
+    float* stats;      // [16][B][2]: per 128-feature tile (sum, sum of squares) of every row of x
     float* part;       // split-K partials [split][B][N] of the swapped tcgen05 decode linears
     size_t bytes;
 };
@@ -433,6 +435,8 @@ static StepWs carve_step(const stb_model* m, int B, void* ws) {
     w.ln = take_split(c, (size_t)B * d, lo);
     w.attn = take_split(c, (size_t)B * d, lo);
     w.hid = take_split(c, (size_t)B * 4 * d, lo);
+    w.xs = take_split(c, (size_t)B * d, lo);
+    w.stats = c.take<float>((size_t)16 * B * 2);
     w.part = (B > step_gemv_max_b() && B <= STEP_SPLITK_MAX_B) ? c.take<float>((size_t)B * STEP_SPLITK_TILES * 128) : nullptr;
     w.bytes = c.off;
     return w;
@@ -453,7 +457,6 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     const void* const(*t)[2] = m->t;
     StepWs w = carve_step(m, B, ws);
     const size_t cache = (size_t)B * ctx * d;
-    STB_TRY(embed_step(tokens, pos, seq_off, D.n_text_ctx, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0], (const float*)t[STB_T_DEC_POS][0], w.x, st));
     const void* emb_hi = t[STB_T_DEC_TOKEMB][0];
     const void* emb_lo = m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr;
     // Linear layers of the step, by batch size:
@@ -478,15 +481,29 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
         explicit PriorityScope(int p) : saved(launch_priority()) { launch_priority() = p; }
         ~PriorityScope() { launch_priority() = saved; }
     };
+    // LayerNorm folded into the consumer linears (decode_linear.cu, DLFuse): only on the cluster-kernel route, only when the
+    // folded weights were supplied for every layer and the width is a whole number of 128-feature tiles
+    bool fused_ln = option(OPT_DECODE_FUSED_LN) != 0 && use_splitk && !legacy_splitk && d % 128 == 0 && d / 128 <= 16 &&
+                    t[STB_T_DEC_TOKEMB_G][0] != nullptr && t[STB_T_DEC_TOKEMB_FOLD][0] != nullptr;
+    for (int l = 0; fused_ln && l < D.n_text_layer; ++l)
+        for (int id = STB_L_QKV_WG; id < STB_L_COUNT; ++id)
+            if (m->dec[l].p[id][0] == nullptr) fused_ln = false;
+    STB_TRY(embed_step(tokens, pos, seq_off, D.n_text_ctx, B, d, (const float*)t[STB_T_DEC_TOKEMB_F32][0],
+                       (const float*)t[STB_T_DEC_POS][0], w.x, fused_ln ? w.xs.hi : nullptr, fused_ln ? w.xs.lo : nullptr,
+                       fused_ln ? w.stats : nullptr, st));
     auto lin = [&](const Split& x, int k, const void* w_hi, const void* w_lo, int n, const float* bias, int act,
                    const float* res, float* out_f32, Split out_split, long long ld, const float* ln_g,
-                   const float* ln_b) -> int {
+                   const float* ln_b, const DLFuse* fuse = nullptr) -> int {
         PriorityScope prio(lin_priority);
+        if (fuse != nullptr) {                                 // fused route: always the cluster kernel
+            STB_REQUIRE(use_splitk && !legacy_splitk && k % 64 == 0 && n >= 128, "decode_step: folded LayerNorm off the cluster route");
+            return decode_linear(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, fuse, st);
+        }
         if (use_gemv) {
             STB_TRY(gemv(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st));
         } else if (use_splitk && !legacy_splitk && k % 64 == 0 && n >= 128) {
             // one launch: cluster split-K + DSMEM reduction + fused epilogue (decode_linear.cu)
-            STB_TRY(decode_linear(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, st));
+            STB_TRY(decode_linear(x.hi, x.lo, B, k, w_hi, w_lo, n, bias, act, res, ld, out_f32, out_split.hi, out_split.lo, ld, nullptr, st));
         } else if (use_splitk) {
             const int mt = cdiv(n, 128), nkb = k / 64;
             int split = 1;
@@ -528,6 +545,55 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     };
     const float* final_g = (const float*)t[STB_T_DEC_LN_G][0];
     const float* final_b = (const float*)t[STB_T_DEC_LN_B][0];
+    if (fused_ln) {
+        // x (fp32) + its split planes + per-tile row statistics travel from producer to consumer; every LayerNorm is the
+        // consumer's epilogue: 8 launches per layer instead of 11
+        const int tiles_d = d / 128;
+        const bool x3 = m->prec == STB_PREC_FP16X3;
+        int tiles_in = 1;                                      // embed_step left full-row sums
+        auto fold = [&](const stb_model::Layer& L, int wg, int fd, int n, DLFuse& f, const void*& whi, const void*& wlo,
+                        const float*& cb) {
+            whi = L.p[wg][0];
+            wlo = x3 ? L.p[wg][1] : nullptr;
+            const float* fp = (const float*)L.p[fd][0];
+            f.stats_in = w.stats; f.tiles_in = tiles_in; f.row_features = d; f.wsum = fp; f.stats_out = nullptr;
+            cb = fp + n;
+        };
+        for (int l = 0; l < D.n_text_layer; ++l) {
+            const stb_model::Layer& L = m->dec[l];
+            float* Kc = (float*)state + (size_t)l * 2 * cache;
+            float* Vc = Kc + cache;
+            DLFuse f, prod = {nullptr, 0, 0, nullptr, w.stats};
+            const void *whi, *wlo;
+            const float* cb;
+            fold(L, STB_L_QKV_WG, STB_L_QKV_FOLD, 3 * d, f, whi, wlo, cb);
+            STB_TRY(lin(w.xs, d, whi, wlo, 3 * d, cb, STB_ACT_NONE, nullptr, w.qkv, none, 3 * d, nullptr, nullptr, &f));
+            STB_TRY(decode_attn_self(w.qkv, Kc, Vc, B, H, d, ctx, pos, seq_off, w.attn.hi, w.attn.lo, nullptr, st));
+            STB_TRY(lin(w.attn, d, W_HI(L, STB_L_OUT_W), W_LO(L, STB_L_OUT_W), d, W_F32(L, STB_L_OUT_B), STB_ACT_NONE, w.x, w.x,
+                        w.xs, d, nullptr, nullptr, &prod));
+            tiles_in = tiles_d;
+            fold(L, STB_L_CQ_WG, STB_L_CQ_FOLD, d, f, whi, wlo, cb);
+            STB_TRY(lin(w.xs, d, whi, wlo, d, cb, STB_ACT_NONE, nullptr, w.q, none, d, nullptr, nullptr, &f));
+            Split Kx, vTx;
+            CrossDecodeKV Vd;
+            cross_ptrs(m, kv_total, ckv, l, Kx, vTx, &Vd);
+            Vd.k_hi += (size_t)kv_off * H * STB_N_AUDIO_CTX * 64;
+            Vd.v_hi += (size_t)kv_off * H * STB_N_AUDIO_CTX * 64;
+            STB_TRY(decode_attn_cross(w.q, Vd, B, H, d, w.xpart, w.tickets, w.attn.hi, w.attn.lo, nullptr, st));
+            STB_TRY(lin(w.attn, d, W_HI(L, STB_L_COUT_W), W_LO(L, STB_L_COUT_W), d, W_F32(L, STB_L_COUT_B), STB_ACT_NONE, w.x,
+                        w.x, w.xs, d, nullptr, nullptr, &prod));
+            fold(L, STB_L_FC1_WG, STB_L_FC1_FOLD, 4 * d, f, whi, wlo, cb);
+            STB_TRY(lin(w.xs, d, whi, wlo, 4 * d, cb, STB_ACT_GELU, nullptr, nullptr, w.hid, 4 * d, nullptr, nullptr, &f));
+            STB_TRY(lin(w.hid, 4 * d, W_HI(L, STB_L_FC2_W), W_LO(L, STB_L_FC2_W), d, W_F32(L, STB_L_FC2_B), STB_ACT_NONE, w.x, w.x,
+                        w.xs, d, nullptr, nullptr, &prod));
+        }
+        DLFuse f = {w.stats, tiles_in, d, (const float*)t[STB_T_DEC_TOKEMB_FOLD][0], nullptr};
+        const float* cbv = (const float*)t[STB_T_DEC_TOKEMB_FOLD][0] + D.n_vocab;
+        STB_TRY(lin(w.xs, d, t[STB_T_DEC_TOKEMB_G][0], x3 ? t[STB_T_DEC_TOKEMB_G][1] : nullptr, D.n_vocab, cbv, STB_ACT_NONE, nullptr,
+                    logits, none, ld_logits, nullptr, nullptr, &f));
+        STB_TRY(bump_pos(pos, st));
+        return STB_OK;
+    }
     if (D.n_text_layer > 0)
         STB_TRY(layernorm(w.x, B, d, W_F32(m->dec[0], STB_L_ATTN_LN_G), W_F32(m->dec[0], STB_L_ATTN_LN_B), w.ln.hi, w.ln.lo, nullptr, st));
     else
@@ -642,7 +708,7 @@ static int check_weights(const stb_model* m, bool enc, bool dec) {
         STB_TRY(need(m->t[STB_T_DEC_LN_G], false, "dec.ln.g", -1));
         STB_TRY(need(m->t[STB_T_DEC_LN_B], false, "dec.ln.b", -1));
         for (size_t l = 0; l < m->dec.size(); ++l)
-            for (int id = 0; id < STB_L_COUNT; ++id) STB_TRY(need(m->dec[l].p[id], is_split(id), "dec.layer", (int)l));
+            for (int id = 0; id < STB_L_QKV_WG; ++id) STB_TRY(need(m->dec[l].p[id], is_split(id), "dec.layer", (int)l));   // *_WG / *_FOLD are optional
     }
     return STB_OK;
 }

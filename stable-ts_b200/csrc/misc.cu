@@ -68,6 +68,9 @@ static const OptDef g_opt_defs[OPT_COUNT] = {
     {"decode_lin_priority", "STB_DECODE_LIN_PRIORITY", 1},
     // 1: decode-step cross-attention on the warp-level tensor cores (ldmatrix + mma.sync over TMA-swizzled K / V tiles)
     {"xattn_tc", "STB_XATTN_TC", 1},
+    // 1: the decode step folds every LayerNorm into the Linear that follows it (W diag(g) planes + row statistics from the
+    // producer's epilogue); needs the optional STB_L_*_WG / *_FOLD tensors, else the step runs its LayerNorm kernels
+    {"decode_fused_ln", "STB_DECODE_FUSED_LN", 0},
 };
 static int g_opt[OPT_COUNT];
 static bool g_opt_init = false;

@@ -82,7 +82,8 @@ class B200Whisper(WhisperProtocol):
     protocol / ``detect_language``) that the unmodified reference code drives."""
 
     def __init__(self, dims, state_dict: Dict[str, torch.Tensor], device: Union[str, torch.device] = "cuda",
-                 precision: str = "fp16x3", alignment_heads: Optional[Sequence[Tuple[int, int]]] = None):
+                 precision: str = "fp16x3", alignment_heads: Optional[Sequence[Tuple[int, int]]] = None,
+                 fold_layernorm: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("B200Whisper needs a CUDA device (there is no CPU fallback)")
         self.dims = ModelDimensions(**{k: int(getattr(dims, k)) for k in ModelDimensions.__dataclass_fields__})
@@ -90,6 +91,9 @@ class B200Whisper(WhisperProtocol):
         self.precision = precision
         self._prec = {"fp16x3": L.STB_PREC_FP16X3, "fp16": L.STB_PREC_FP16}[precision]
         self._want_lo = self._prec == L.STB_PREC_FP16X3
+        # also pack W diag(gamma) planes + fold vectors of the decoder linears that follow a LayerNorm: the decode step can
+        # then fold the LayerNorm into the Linear (option "decode_fused_ln"; +8 d^2 + V d weights, 1.9 GB at large-v3)
+        self.fold_layernorm = bool(fold_layernorm)
         self._keep: List[torch.Tensor] = []
         self._ws: Dict[str, torch.Tensor] = {}
         self.graph_kernel_launches = 0     # kernels executed by CUDA-graph replays (the library counter only sees captures)
@@ -160,6 +164,21 @@ class B200Whisper(WhisperProtocol):
     def _set_f32(self, tid, is_dec, layer, w: torch.Tensor):
         self._set(tid, is_dec, layer, self._dev(w.float()))
 
+    def _set_folded(self, tid_w, tid_fold, is_dec, layer, w: torch.Tensor, bias: Optional[torch.Tensor], gamma: torch.Tensor,
+                    beta: torch.Tensor):
+        """LayerNorm (gamma, beta) folded into the Linear (w, bias) that follows it, for the decode step (STB_L_*_WG / *_FOLD):
+        planes of W diag(gamma); fold = [row sums of exactly those planes | W beta + bias].  The sums are taken from the fp16
+        planes (what the tensor core multiplies), in float64, so that `acc - mean * rowsum` cancels the way the GEMM adds."""
+        w = w.to(self.device).float()
+        wg = w * gamma.to(self.device).float()[None, :]
+        hi, lo = _split(wg, self._want_lo)
+        rows = hi.double().sum(1) if lo is None else (hi.double() + lo.double()).sum(1)
+        cb = w.double() @ beta.to(self.device).double()
+        if bias is not None:
+            cb = cb + bias.to(self.device).double()
+        self._set(tid_w, is_dec, layer, self._dev(hi), self._dev(lo) if lo is not None else None)
+        self._set(tid_fold, is_dec, layer, self._dev(torch.stack([rows, cb]).float()))
+
     def _pack(self, sd: Dict[str, torch.Tensor]):
         D = self.dims
         g = lambda k: sd[k].detach().float()
@@ -199,6 +218,15 @@ class B200Whisper(WhisperProtocol):
                 self._set_f32(B + L.L_CKV_B, 1, l, torch.cat([z, g(p + "cross_attn.value.bias")]))
                 self._set_split(B + L.L_COUT_W, 1, l, g(p + "cross_attn.out.weight"))
                 self._set_f32(B + L.L_COUT_B, 1, l, g(p + "cross_attn.out.bias"))
+                if self.fold_layernorm:
+                    self._set_folded(B + L.L_QKV_WG, B + L.L_QKV_FOLD, 1, l,
+                                     torch.cat([g(p + "attn.query.weight"), g(p + "attn.key.weight"), g(p + "attn.value.weight")]),
+                                     torch.cat([g(p + "attn.query.bias"), z, g(p + "attn.value.bias")]),
+                                     g(p + "attn_ln.weight"), g(p + "attn_ln.bias"))
+                    self._set_folded(B + L.L_CQ_WG, B + L.L_CQ_FOLD, 1, l, g(p + "cross_attn.query.weight"),
+                                     g(p + "cross_attn.query.bias"), g(p + "cross_attn_ln.weight"), g(p + "cross_attn_ln.bias"))
+                    self._set_folded(B + L.L_FC1_WG, B + L.L_FC1_FOLD, 1, l, g(p + "mlp.0.weight"), g(p + "mlp.0.bias"),
+                                     g(p + "mlp_ln.weight"), g(p + "mlp_ln.bias"))
 
         for l in range(D.n_audio_layer):
             block("encoder", 0, l, D.n_audio_state)
@@ -210,6 +238,8 @@ class B200Whisper(WhisperProtocol):
         self._set_f32(L.T_DEC_POS, 0, 0, g("decoder.positional_embedding"))
         self._set_f32(L.T_DEC_LN_G, 0, 0, g("decoder.ln.weight"))
         self._set_f32(L.T_DEC_LN_B, 0, 0, g("decoder.ln.bias"))
+        if self.fold_layernorm:
+            self._set_folded(L.T_DEC_TOKEMB_G, L.T_DEC_TOKEMB_FOLD, 0, 0, emb, None, g("decoder.ln.weight"), g("decoder.ln.bias"))
 
     def _frontend_tables(self):
         n = np.arange(400, dtype=np.float64)
