@@ -662,6 +662,7 @@ def run_b200(args, dims_tuple):
                          "[2, 480000] + script of 442 / 442 / 116 tokens -> probabilities and ranks (BASELINE config 5 shape)"),
                    "weights": "seeded random init at true shapes", "precision": args.precision,
                    "alignment_heads": args.alignment_heads,
+                   "kernel_options": {k: L.get_option(k) for k in ("decode_splitk_legacy", "xattn_tc", "decode_fused_ln")},
                    "l2": "per-step working set (weights 6.2 GB + activations) >> 126 MB L2; inputs rotate between 2 pools"},
         "rtf": 1.0 / value, "aligned_words_per_s": n_words_total / (ms_step / 1e3),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_other": roof_other, "kernels": kernels,

@@ -156,7 +156,7 @@ enum {
     STB_T_DEC_LN_B,
     /* optional, decode step with the final LayerNorm folded into the vocabulary projection (see STB_L_*_WG below) */
     STB_T_DEC_TOKEMB_G,    /* split [V][d]: token embedding * ln.weight (column-wise) */
-    STB_T_DEC_TOKEMB_FOLD, /* f32 [2][V]: row sums of the split planes | emb . ln.bias */
+    STB_T_DEC_TOKEMB_FOLD, /* f32 [2][V4], V4 = V rounded up to 4: row sums of the split planes | emb . ln.bias */
     STB_T_LAYER_BASE = 32,
     /* per-layer ids (add to STB_T_LAYER_BASE); encoder layers use ENC_*, decoder layers DEC_* */
     STB_L_ATTN_LN_G = 0, STB_L_ATTN_LN_B, STB_L_QKV_W /* split [3d][d]: q,k,v */, STB_L_QKV_B /* f32 [3d], k part 0 */,
@@ -167,7 +167,7 @@ enum {
      * y = rstd (W' x - mean * rowsum(W')) + (W beta + bias): the step's GEMM runs on the raw residual stream x, its epilogue
      * applies the row statistics that the PRODUCER of x left behind -- no LayerNorm launch (3 per layer) in the step.
      *   *_WG    split [n][d]   W' (hi / lo planes)
-     *   *_FOLD  f32 [2][n]     rowsum of the planes (what the tensor core multiplies) | W beta + bias */
+     *   *_FOLD  f32 [2][n4]    n4 = n rounded up to 4: rowsum of the planes (what the tensor core multiplies) | W beta + bias */
     STB_L_QKV_WG, STB_L_QKV_FOLD, STB_L_CQ_WG, STB_L_CQ_FOLD, STB_L_FC1_WG, STB_L_FC1_FOLD,
     STB_L_COUNT
 };

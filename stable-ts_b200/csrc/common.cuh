@@ -11,6 +11,15 @@
 
 #include "../../include/stablets_b200.h"
 
+// NO kernel parameter of this library is restrict-qualified.  Under programmatic dependent launch a kernel reads its
+// predecessor's output after griddepcontrol.wait; with `const T* __restrict__` parameters nvcc turns such reads into
+// ld.global.nc, and -- invariant loads carry no memory dependence -- schedules them ABOVE the wait (round 2, seen in SASS:
+// LDG.E.CONSTANT of the token id and of the position counter before ACQBULK in embed_step_kernel; under CUDA-graph replay
+// the step then embedded the PREVIOUS token).  The qualifier stays in the sources as documentation of intent and is erased
+// here; data that really is constant for a kernel's lifetime (weights, biases, tables) is read with explicit __ldg().
+// tools/check_pdl_sass.py lists every non-coherent load that precedes a kernel's wait.
+#define __restrict__
+
 namespace stb {
 
 // ---- host-side error plumbing (thread-local message returned by stb_last_error) ----

@@ -557,7 +557,7 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
             wlo = x3 ? L.p[wg][1] : nullptr;
             const float* fp = (const float*)L.p[fd][0];
             f.stats_in = w.stats; f.tiles_in = tiles_in; f.row_features = d; f.wsum = fp; f.stats_out = nullptr;
-            cb = fp + n;
+            cb = fp + ((n + 3) & ~3);                          // *_FOLD is f32 [2][n rounded up to 4]
         };
         for (int l = 0; l < D.n_text_layer; ++l) {
             const stb_model::Layer& L = m->dec[l];
@@ -588,7 +588,7 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
                         w.xs, d, nullptr, nullptr, &prod));
         }
         DLFuse f = {w.stats, tiles_in, d, (const float*)t[STB_T_DEC_TOKEMB_FOLD][0], nullptr};
-        const float* cbv = (const float*)t[STB_T_DEC_TOKEMB_FOLD][0] + D.n_vocab;
+        const float* cbv = (const float*)t[STB_T_DEC_TOKEMB_FOLD][0] + ((D.n_vocab + 3) & ~3);
         STB_TRY(lin(w.xs, d, t[STB_T_DEC_TOKEMB_G][0], x3 ? t[STB_T_DEC_TOKEMB_G][1] : nullptr, D.n_vocab, cbv, STB_ACT_NONE, nullptr,
                     logits, none, ld_logits, nullptr, nullptr, &f));
         STB_TRY(bump_pos(pos, st));

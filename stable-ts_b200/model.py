@@ -177,7 +177,11 @@ class B200Whisper(WhisperProtocol):
         if bias is not None:
             cb = cb + bias.to(self.device).double()
         self._set(tid_w, is_dec, layer, self._dev(hi), self._dev(lo) if lo is not None else None)
-        self._set(tid_fold, is_dec, layer, self._dev(torch.stack([rows, cb]).float()))
+        n_pad = (rows.numel() + 3) // 4 * 4                   # both vectors start 16-byte aligned (V = 51866 is not a multiple of 4)
+        fold = torch.zeros(2, n_pad, dtype=torch.float32, device=rows.device)
+        fold[0, : rows.numel()] = rows.float()
+        fold[1, : rows.numel()] = cb.float()
+        self._set(tid_fold, is_dec, layer, self._dev(fold))
 
     def _pack(self, sd: Dict[str, torch.Tensor]):
         D = self.dims
