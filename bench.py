@@ -37,6 +37,25 @@ AUDIO_S = 30.0
 N_SAMPLES = 480000
 
 
+# stdout carries exactly ONE line, the JSON result: the process's real stdout is kept aside and file descriptor 1 is pointed at
+# stderr for everything else (NCCL prints its version banner on stdout, libraries and warnings may print too)
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
@@ -342,7 +361,7 @@ def run_reference(args, dims_tuple):
                                        if kind == "reference" else f"oracle port of the reference CPU path ({why_port})"))},
         "e2e": {"value": value, "unit": "audio_s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def parity_refine(p, r, cpu):
@@ -675,11 +694,12 @@ def run_b200(args, dims_tuple):
                                           + (Wn * (2 * args.tokens * 4 + 24 + 4) if args.workload == "transcribe" else 0)),
                 "ms_per_step": e2e_s * 1e3, "aligned_words_per_s": n_words_total / e2e_s},
     }
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def main():
     args = parse()
+    claim_stdout()
     from stable_ts_b200.api import MODEL_DIMS
     dims_tuple = MODEL_DIMS[args.model]
     if args.impl == "reference":
