@@ -243,8 +243,11 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
     if language is None:
         language = "en" if not model.is_multilingual else model.detect_language_of(wave[:480000])
     tk = tokenizer or get_tokenizer(model, language=language, task=task, synthetic=getattr(model, "random_init", False))
+    unknown = sorted(k for k in decode_options if k not in DecodingOptions.__dataclass_fields__)
+    if unknown:                                        # the reference hands them to DecodingOptions(**kwargs), which raises too
+        raise TypeError(f"transcribe() got unexpected decoding option(s): {unknown}")
     opts = DecodingOptions(task=task, language=language, max_initial_timestamp=decode_options.pop("max_initial_timestamp", None),
-                           **{k: v for k, v in decode_options.items() if k in DecodingOptions.__dataclass_fields__})
+                           **decode_options)
     d = run(model, tk, wave, batch_windows=batch_windows, shard_seconds=shard_seconds, word_timestamps=word_timestamps,
             options=opts, suppress_ts_tokens=suppress_ts_tokens, q_levels=q_levels, k_size=k_size,
             no_speech_threshold=no_speech_threshold, logprob_threshold=logprob_threshold, max_instant_words=max_instant_words,

@@ -310,3 +310,38 @@ def test_layernorm_folded_into_the_step_linears():
                 assert a.tokens == b.tokens
     finally:
         L.set_option("decode_fused_ln", default)
+
+
+def test_splitk_finish_linears_option_matches_cluster_linears():
+    """Option "decode_splitk_legacy": the round-1 route of the decode-step linears (swapped split-K tcgen05 GEMM with partials in
+    L2 + finish kernel with the fused LayerNorm) against the cluster kernel: same step logits and tokens."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from oracle import stable_path as SP
+    from oracle.whisper_ref.model import ModelDimensions
+    from stable_ts_b200 import _lib as L
+    from stable_ts_b200.decode import DecodingOptions, decode_windows
+    dims = ModelDimensions(n_mels=128, n_audio_ctx=1500, n_audio_state=1280, n_audio_head=20, n_audio_layer=1, n_vocab=51866,
+                           n_text_ctx=448, n_text_state=1280, n_text_head=20, n_text_layer=2)
+    W, model, gm, tk = _mk(dims, 31)
+    audios = torch.stack([SP.synth_audio(480000, seed=500 + i) for i in range(3)])
+    enc = gm.encode(gm.log_mel(audios.repeat(14, 1).cuda()))          # B = 42
+    opt = DecodingOptions(sample_len=6)
+    default = L.get_option("decode_splitk_legacy")
+    try:
+        L.set_option("decode_splitk_legacy", 0)
+        r0, x0 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
+        L.set_option("decode_splitk_legacy", 1)
+        r1, x1 = decode_windows(gm, tk, enc, opt, return_step_logits=True)
+        worst = 0.0
+        for a, b in zip(x0["step_logits"], x1["step_logits"]):
+            a, b = a.float().cpu(), b.float().cpu()
+            fin = a > -1e30
+            assert torch.equal(fin, b > -1e30)
+            worst = max(worst, ((a[fin] - b[fin]).abs().max() / a[fin].abs().max()).item())
+        print(f"B=42: split-K + finish vs cluster linears, worst step-logit rel diff {worst:.2e}")
+        assert worst < 2e-5
+        for a, b in zip(r0, r1):
+            assert a.tokens == b.tokens
+    finally:
+        L.set_option("decode_splitk_legacy", default)
