@@ -3,15 +3,21 @@
 N B200s of one node.
 
     python bench.py [--gpus N --steps K --warmup W]              # this repo's B200 path (N>1: launched by torchrun)
-    python bench.py --impl reference [...]                       # the reference's CPU path (oracle port) on host cores
+    python bench.py --impl reference [...]                       # the reference's CPU path on the host cores: the UNMODIFIED
+                                                                 # transcribe_stable (baseline/_ref) over the oracle's whisper
+                                                                 # restatement, else the oracle port
+    python bench.py --model small --workload align --windows 64  # BASELINE config 3;  --model base --windows 1: config 2;
+    python bench.py --workload refine                            # config 5
 
-One "step" = one pass of the hot path over one batch of synthetic 30 s windows per GPU:
-    log-mel -> encoder -> cross K/V -> teacher-forced decoder with cross-attention capture -> token probabilities
-    -> QK post-processing -> DTW -> word timings            (stable_whisper `align` per-window math)
+One "step" (default workload, BASELINE configs 2/4 shape) = one pass of the hot path over one batch of synthetic 30 s
+windows per GPU:
+    log-mel -> encoder -> cross K/V -> 224 KV-cached decode steps (filters + pick, fixed token script) -> segment slicing ->
+    teacher-forced decoder with cross-attention capture -> token probabilities -> QK post-processing -> DTW -> word timings
 `value` times the device pipeline with inputs resident in HBM (CUDA events); `e2e` times the public API call
-(`stable_ts_b200.alignment.align_words_batch`) from pinned HOST audio to host word lists, including the final
-all-gather of word records when N > 1.  Weights are seeded random init at the true large-v3 shapes (no checkpoints
-offline); token scripts are seeded synthetic ids.
+(`stable_ts_b200.transcribe.transcribe_windows` through `sharding.run_sharded`) from pinned HOST audio to host word lists,
+including the final all-gather of word records when N > 1.  Weights are seeded random init at the true shapes (no
+checkpoints offline); token scripts are seeded synthetic ids.  stdout carries exactly the one JSON
+line; everything else goes to stderr.
 """
 import argparse
 import json

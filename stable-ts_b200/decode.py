@@ -1,8 +1,10 @@
-"""Host-side mirror of stable_whisper/decode.py for the B200 path: KV-cached greedy decoding of a BATCH of windows.
+"""Host-side mirror of stable_whisper/decode.py for the B200 path: KV-cached decoding of a BATCH of windows -- greedy at
+temperature 0, ``best_of`` draws at temperature > 0, the temperature fallback of ``transcribe_stable`` over batch subsets,
+per-window prompts (ragged initial tokens).
 
 ``decode_stable`` keeps the reference's call shape for one window; ``decode_windows`` is the batched engine:
     encoder output (cached, as DecodingTaskStable._get_audio_features) -> cross K/V ->
-    per step: [fused logit filters + greedy pick] -> [decoder step for B sequences]     (decode.py:33-65)
+    per step: [fused logit filters + pick / draw] -> [decoder step for B sequences]     (decode.py:33-65)
 The two kernels-sequences of a step are captured ONCE into a CUDA graph and replayed; every position-dependent value
 lives in device memory (position counter, per-sequence sampling state, token/argmax tables indexed by step), so the
 host only polls the `done` flags every few steps instead of the reference's per-step ``.all()`` sync.

@@ -58,6 +58,13 @@ def test_ragged_prompts_and_caps_match_oracle_window_by_window(env):
         ref, _, _ = SP.decode_window(om, mel, language="en", sample_len=12, prompt=p or None)
         assert res[b].tokens == ref.tokens
         assert abs(res[b].avg_logprob - ref.avg_logprob) < 1e-4 and abs(res[b].no_speech_prob - ref.no_speech_prob) < 1e-6
+    # prefix of the current context (DecodingTask._get_initial_tokens) together with a prompt, ragged over the batch
+    prefix = torch.randint(300, 40000, (4,), generator=g).tolist()
+    res, ex = decode_windows(stand, tk, enc, DecodingOptions(language="en", sample_len=10, prefix=prefix), prompts=prompts)
+    for b, (a, p) in enumerate(zip(audios, prompts)):
+        mel = W.pad_or_trim(W.log_mel_spectrogram(a, om.dims.n_mels), 3000)
+        ref, _, _ = SP.decode_window(om, mel, language="en", sample_len=10, prompt=p or None, prefix=prefix)
+        assert res[b].tokens == ref.tokens and abs(res[b].avg_logprob - ref.avg_logprob) < 1e-4
     # n_ctx stop (decode.py:60): 1 + 223 + 1 = 225 initial tokens (tiny.en: sot_sequence is one token) leave room for 224 samples
     # although sample_len is 230; the neighbour without a prompt runs the full script
     forced = torch.randint(300, 40000, (230, 2), generator=g, dtype=torch.int32)
