@@ -2,11 +2,12 @@
 // kv-cache hooks, the logit filters, GreedyDecoder.update).
 //
 //   stb_decode_step     one decoder forward for the newest token of B sequences (engine.cu: decode_step).  Linear layers:
-//                       mma.sync batched GEMV (gemv.cu) up to 16 sequences, swapped split-K tcgen05 GEMM + fused
-//                       finish/LayerNorm up to 128.  Attention over the caches runs on CUDA cores in this file (one query
-//                       row per (sequence, head): no tensor-core shape), flash-decoding style, HBM-bound by the cross K/V.
-//   stb_sample_greedy   SuppressBlank / SuppressTokens / ApplyTimestampRules / silent-timestamp mask / argmax /
-//                       log-prob accumulation / EOT latching fused into one kernel per step, state kept on the device.
+//                       mma.sync batched GEMV (gemv.cu) up to 16 sequences, the cluster split-K tcgen05 kernel of
+//                       decode_linear.cu up to 128.  Attention over the caches is in this file, flash-decoding style: the
+//                       cross-attention (HBM-bound by the fp16 cross K/V, the largest stream of a step) on ldmatrix +
+//                       mma.sync over TMA-swizzled tiles, the self-attention over the fp32 cache on scalar lanes.
+//   stb_sample          SuppressBlank / SuppressTokens / ApplyTimestampRules / silent-timestamp mask / argmax or inverse-CDF
+//                       draw / log-prob accumulation / EOT latching fused into one kernel per step, state kept on the device.
 //
 // Everything position-dependent is read from a DEVICE counter (`pos`), so one captured CUDA graph replays every step.
 #include <float.h>

@@ -461,10 +461,11 @@ static int decode_step(stb_model* m, const int32_t* tokens, int B, int32_t* pos,
     const void* emb_lo = m->prec == STB_PREC_FP16X3 ? t[STB_T_DEC_TOKEMB][1] : nullptr;
     // Linear layers of the step, by batch size:
     //   B <= 16      : latency-optimised batched GEMV (mma.sync, gemv.cu) -- one launch, weights straight into fragments
-    //   17 .. 128    : SWAPPED split-K tcgen05 GEMM: the features take the 128-row M side (every weight byte is read by
-    //                  exactly one CTA), the sequences the N side (BN = 32/64/128), and the K range is cut into `split`
-    //                  slices on the GEMM batch axis so that ~one tile lands on every SM; partials [split][B][N] stay in
-    //                  L2 and splitk_finish_kernel adds bias / GELU / residual and the LayerNorm that follows
+    //   17 .. 128    : SWAPPED tcgen05 GEMM: the features take the 128-row M side (every weight byte is read by exactly
+    //                  one CTA), the sequences the N side (BN = 32/64/128).  Default: decode_linear.cu -- split-K across a
+    //                  thread-block cluster, partial tiles reduced over distributed shared memory, fused epilogue, ONE
+    //                  launch.  Option decode_splitk_legacy (round 1): the K range cut into `split` slices on the GEMM batch
+    //                  axis, partials [split][B][N] in L2, splitk_finish_kernel adds bias / GELU / residual / LayerNorm
     //   > 128        : the plain tcgen05 GEMM (sequences on the M side)
     const bool use_gemv = B <= step_gemv_max_b(), use_splitk = !use_gemv && B <= STEP_SPLITK_MAX_B;
     static const int tile_budget = env_int("STB_STEP_SPLIT_TILES", sm_count(), 1, STEP_SPLITK_TILES);
