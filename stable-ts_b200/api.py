@@ -219,7 +219,7 @@ def _set_language(result, tokenizer, language):
 
 
 def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, task: str = "transcribe", word_timestamps: bool = True,
-               regroup=True, suppress_ts_tokens: bool = False, q_levels: int = 20, k_size: int = 5,
+               regroup=True, suppress_silence: bool = True, suppress_ts_tokens: bool = False, q_levels: int = 20, k_size: int = 5,
                temperature: Union[float, Tuple[float, ...]] = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0),
                compression_ratio_threshold: Optional[float] = 2.4, no_speech_threshold: Optional[float] = 0.6,
                logprob_threshold: Optional[float] = -1.0, condition_on_previous_text: bool = True,
@@ -230,7 +230,10 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
     ``batch_windows`` at a time (transcribe.py); ``shard_seconds=None`` walks the audio as one sequential shard like the
     reference.  Decoding defaults are the reference's: the temperature fallback sequence with its compression-ratio /
     log-prob / no-speech tests, ``best_of`` draws at temperature > 0, the previous window's text as the prompt of the next
-    (inside a shard).  ``generator`` / ``uniforms``: random stream of the temperature > 0 passes (decode.decode_with_fallback).
+    (inside a shard).  ``suppress_silence``: as in the reference (original_whisper.py:428) the non-VAD silence detector only
+    runs when it is True -- silent windows are then skipped and ``suppress_ts_tokens`` masks the silent timestamp tokens; the
+    reference's word re-timing against the silence (``Segment.suppress_silence``, result.py) is outside this package's scope
+    and NOT applied.  ``generator`` / ``uniforms``: random stream of the temperature > 0 passes (decode.decode_with_fallback).
     Beam search is not implemented."""
     from .decode import DecodingOptions
     from .tokenizer import get_tokenizer
@@ -249,7 +252,8 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
     opts = DecodingOptions(task=task, language=language, max_initial_timestamp=decode_options.pop("max_initial_timestamp", None),
                            **decode_options)
     d = run(model, tk, wave, batch_windows=batch_windows, shard_seconds=shard_seconds, word_timestamps=word_timestamps,
-            options=opts, suppress_ts_tokens=suppress_ts_tokens, q_levels=q_levels, k_size=k_size,
+            options=opts, suppress_ts_tokens=bool(suppress_ts_tokens and suppress_silence), skip_silent=bool(suppress_silence),
+            q_levels=q_levels, k_size=k_size,
             no_speech_threshold=no_speech_threshold, logprob_threshold=logprob_threshold, max_instant_words=max_instant_words,
             gap_padding=gap_padding, min_word_dur=min_word_dur, temperature=temperature,
             compression_ratio_threshold=compression_ratio_threshold, condition_on_previous_text=condition_on_previous_text,

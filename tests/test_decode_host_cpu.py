@@ -138,3 +138,24 @@ def test_transcribe_fallback_prompt_and_seek_match_unmodified_reference(env, tem
         assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
         for wa, wb in zip(sa["words"], sb["words"]):
             assert wa["start"] == wb["start"] and wa["end"] == wb["end"]
+
+
+def test_transcribe_with_silence_masks_matches_unmodified_reference(env):
+    """``suppress_ts_tokens=True`` (per-window non-VAD silence mask -> timestamp-token mask of the sampler, original_whisper.py:
+    504-511; silent-window fast-forward :508-510) over audio with silent gaps, sequential walk, temperature 0.  The reference
+    only runs its silence detector with ``suppress_silence=True`` (``vad=vad if suppress_silence else None``, :428), which also
+    re-times the words afterwards (``Segment.suppress_silence``, out of scope here): tokens, seeks and word token groups are
+    compared, not the re-timed word boundaries."""
+    import stable_whisper.whisper_word_level.original_whisper as ow
+    SP, om, stand = env["SP"], env["om"], env["stand"]
+    audio = torch.cat([SP.synth_gapped_audio(480000, seed=61), torch.zeros(200000), SP.synth_gapped_audio(300000, seed=62)])
+    theirs = ow.transcribe_stable(om, audio, language="en", temperature=0.0, condition_on_previous_text=True, word_timestamps=True,
+                                  vad=False, suppress_silence=True, suppress_ts_tokens=True, regroup=False, verbose=None,
+                                  fp16=False, ignore_compatibility=True, sample_len=16)
+    mine = stand.transcribe(audio, language="en", temperature=0.0, condition_on_previous_text=True, regroup=False,
+                            sample_len=16, shard_seconds=None, batch_windows=1, suppress_ts_tokens=True)
+    da, db = mine.to_dict(), theirs.to_dict()
+    assert len(da["segments"]) == len(db["segments"]) and len(da["segments"]) >= 1
+    for sa, sb in zip(da["segments"], db["segments"]):
+        assert sa["tokens"] == [int(t) for t in sb["tokens"]] and sa["seek"] == sb["seek"]
+        assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
