@@ -80,7 +80,8 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                        no_speech_threshold: Optional[float] = None, logprob_threshold: Optional[float] = None,
                        max_instant_words: Optional[float] = None, temperature=0.0,
                        compression_ratio_threshold: Optional[float] = None, prompts=None,
-                       generator: Optional[torch.Generator] = None, uniforms=None):
+                       generator: Optional[torch.Generator] = None, uniforms=None, nonspeech_skip: Optional[float] = None,
+                       avg_prob_threshold: Optional[float] = None):
     """B independent <=30 s windows -> (list (per window) of segment dicts with ``words``, info).
     ``enc`` (+ ``n_samples``) may be passed instead of ``audios`` when the encoder output is already on the device.
 
@@ -91,6 +92,10 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
     temperature (a number or the fallback sequence) / compression_ratio_threshold / logprob_threshold / no_speech_threshold:
     ``decode_with_fallback`` (original_whisper.py:349-393); prompts: per-window previous-context tokens (:533);
     generator / uniforms: the random stream of the temperature > 0 passes (decode.decode_windows).
+    nonspeech_skip: a silence of at least this many seconds ends the window where it starts -- or, when it starts within
+    ``min_word_dur`` of the window start, the window is skipped up to the silence's end (original_whisper.py:512-526).
+    avg_prob_threshold: a window that ends on a single timestamp and whose words average below it is dropped; otherwise the
+    seek moves to the end of the last word (original_whisper.py:665-675,693-694).
     info["advance"][b]: samples the reference's seek would move by after this window (original_whisper.py:703-710)."""
     dev_audio = None
     if enc is None:
@@ -110,15 +115,14 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
             batch = batch.pin_memory()
         with device_ctx(model.device):
             dev_audio = batch.to(model.device, non_blocking=True)
-            mel = model.log_mel(dev_audio)
-            enc = model.encode(mel)
-    B = enc["B"]
+    B = enc["B"] if enc is not None else int(dev_audio.shape[0])
     n_samples = list(n_samples) if n_samples is not None else [N_SAMPLES] * B
     offs = list(time_offsets) if time_offsets is not None else [0.0] * B
     if options is None:                      # transcribe_stable defaults max_initial_timestamp to None (original_whisper.py:262-263)
         options = DecodingOptions(max_initial_timestamp=None)
     silent = [False] * B
-    if suppress_ts_tokens or skip_silent:
+    jump = [None] * B                                        # nonspeech_skip: samples to fast-forward instead of decoding
+    if suppress_ts_tokens or skip_silent or nonspeech_skip:
         if dev_audio is None:
             raise ValueError("silence detection needs the window audio (pass `audios`, not only `enc`)")
         from .silence import predict_nonvad_batch
@@ -132,8 +136,21 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                                                          min_word_dur=min_word_dur)):
                 masks[b] = pred["mask"]
                 silent[b] = bool(pred["is_silent"]) and skip_silent
+                if nonspeech_skip and pred["timings"] is not None and not silent[b]:       # original_whisper.py:512-526
+                    starts, ends = pred["timings"][0] - offs[b], pred["timings"][1] - offs[b]
+                    long_ones = np.flatnonzero((ends - starts) >= nonspeech_skip)
+                    if len(long_ones):
+                        k = long_ones[0]
+                        if starts[k] < (min_word_dur or 0) or int(starts[k] * SAMPLE_RATE) == 0:
+                            jump[b] = round(float(ends[k]) * SAMPLE_RATE)
+                        else:                                 # the window ends where the long silence begins
+                            n_samples[b] = int(starts[k] * SAMPLE_RATE)
+                            dev_audio[b, n_samples[b]:] = 0
         if suppress_ts_tokens and ts_token_mask is None and any(m is not None for m in masks):
             ts_token_mask = masks
+    if enc is None:
+        with device_ctx(model.device):
+            enc = model.encode(model.log_mel(dev_audio))
     # the cross K/V block and the KV cache live in model-owned buffers: they are consumed inside this call (decode loop, then
     # the alignment pass below) and are by far the largest allocations of a step
     results, extras, n_fallback = decode_with_fallback(
@@ -143,11 +160,11 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
         reuse_buffers=True)
     # a re-decode of a subset (or a best_of batch) overwrote the model-owned cross K/V block: the alignment pass rebuilds it
     ckv_valid = not any(n_fallback) and extras.get("n_group", 1) == 1
-    windows, advance, skipped = [], [], []
+    windows, advance, skipped, single = [], [], [], []
     for b in range(B):
         dur = n_samples[b] / SAMPLE_RATE
         toks = results[b].tokens if forced_tokens is None else extras["step_tokens"][:, b].tolist()
-        skip = silent[b]
+        skip = silent[b] or jump[b] is not None
         if not skip and no_speech_threshold is not None:          # original_whisper.py:537-547
             skip = results[b].no_speech_prob > no_speech_threshold
             if logprob_threshold is not None and results[b].avg_logprob > logprob_threshold:
@@ -165,6 +182,7 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
         windows.append(dict(segments=segs, num_samples=num))
         advance.append(n_samples[b] if (skip or single_ending or not len(toks)) else num)
         skipped.append(bool(skip))
+        single.append(bool(single_ending))
     if word_timestamps:
         add_word_timestamps_batch(windows, model, tokenizer, enc=enc, ckv=extras["ckv"] if ckv_valid else None,
                                   gap_padding=gap_padding, min_word_dur=min_word_dur)
@@ -172,9 +190,19 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
             for w in windows:
                 w["segments"] = [s for s in w["segments"] if not s["words"] or float(np.mean(np.array(
                     [x["start"] == x["end"] for x in s["words"]]).astype(np.float16))) <= max_instant_words]
+        if avg_prob_threshold:                                     # original_whisper.py:665-675,693-694
+            for b, w in enumerate(windows):
+                if not w["segments"]:
+                    continue
+                if single[b] and float(np.mean([x["probability"] for s in w["segments"] for x in s["words"]])) < avg_prob_threshold:
+                    w["segments"] = []
+                else:
+                    advance[b] = round((w["segments"][-1]["words"][-1]["end"] - offs[b]) * SAMPLE_RATE)
     for b, w in enumerate(windows):
         if not w["segments"]:
             advance[b] = n_samples[b]                              # nothing kept: the reference fast-forwards the whole window
+        if jump[b] is not None:
+            advance[b] = jump[b]                                   # skipped up to the end of a long leading silence
     return [w["segments"] for w in windows], dict(decode=results, steps=extras["steps"], step_argmax=extras["step_argmax"],
                                                   step_tokens=extras["step_tokens"], advance=advance, skipped=skipped)
 

@@ -159,3 +159,26 @@ def test_transcribe_with_silence_masks_matches_unmodified_reference(env):
     for sa, sb in zip(da["segments"], db["segments"]):
         assert sa["tokens"] == [int(t) for t in sb["tokens"]] and sa["seek"] == sb["seek"]
         assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
+
+
+@pytest.mark.parametrize("opts", [dict(nonspeech_skip=3.0), dict(avg_prob_threshold=0.9), dict(nonspeech_skip=2.0, avg_prob_threshold=1e-9)])
+def test_transcribe_nonspeech_skip_and_avg_prob_threshold_match_unmodified_reference(env, opts):
+    """The two remaining seek controls of the transcribe loop: ``nonspeech_skip`` (a long silence ends the window where it
+    starts, or is skipped when it leads the window; original_whisper.py:512-526) and ``avg_prob_threshold`` (:665-675,693-694).
+    Audio: a long leading silence, speech, a long inner silence, speech.  Tokens, seeks and word groups vs the reference (its
+    silence-based word re-timing is out of scope, see the test above)."""
+    import stable_whisper.whisper_word_level.original_whisper as ow
+    SP, om, stand = env["SP"], env["om"], env["stand"]
+    audio = torch.cat([torch.zeros(90000), SP.synth_audio(150000, seed=71), torch.zeros(100000), SP.synth_audio(260000, seed=72),
+                       torch.zeros(70000), SP.synth_audio(120000, seed=73)])
+    theirs = ow.transcribe_stable(om, audio, language="en", temperature=0.0, condition_on_previous_text=False, word_timestamps=True,
+                                  vad=False, suppress_silence=True, suppress_ts_tokens=False, regroup=False, verbose=None,
+                                  fp16=False, ignore_compatibility=True, sample_len=16, **opts)
+    mine = stand.transcribe(audio, language="en", temperature=0.0, condition_on_previous_text=False, regroup=False,
+                            sample_len=16, shard_seconds=None, batch_windows=1, **opts)
+    da, db = mine.to_dict(), theirs.to_dict()
+    assert [s["seek"] for s in da["segments"]] == [s["seek"] for s in db["segments"]]
+    assert len(da["segments"]) == len(db["segments"])
+    for sa, sb in zip(da["segments"], db["segments"]):
+        assert sa["tokens"] == [int(t) for t in sb["tokens"]]
+        assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
