@@ -207,10 +207,25 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                                                   step_tokens=extras["step_tokens"], advance=advance, skipped=skipped)
 
 
+def clip_sections(clip_timestamps, total: int) -> List[List[int]]:
+    """``clip_timestamps`` ("s0,e0,s1,e1,..." or a flat list of seconds; an odd count leaves the last clip open) ->
+    [[start, end], ...] in samples (original_whisper.py:280-287; audio/__init__.py:431-439: ``round(t * sr)``)."""
+    if isinstance(clip_timestamps, str):
+        clip_timestamps = [float(t) for t in (clip_timestamps.split(",") if clip_timestamps else [])]
+    ts = list(clip_timestamps or [])
+    pairs = [ts[i:i + 2] for i in range(0, len(ts), 2)]
+    out = []
+    for p in pairs:
+        lo = round(p[0] * SAMPLE_RATE) if p[0] is not None else 0
+        hi = round(p[1] * SAMPLE_RATE) if len(p) == 2 and p[1] is not None else total
+        out.append([max(lo, 0), min(hi, total)])
+    return out
+
+
 def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_windows: int = 16, shard_seconds: Optional[float] = 30.0,
                no_speech_threshold: Optional[float] = 0.6, logprob_threshold: Optional[float] = -1.0,
                max_instant_words: Optional[float] = 0.5, skip_silent: bool = True, condition_on_previous_text: bool = False,
-               initial_prompt: Optional[str] = None, **kw) -> dict:
+               initial_prompt: Optional[str] = None, clip_timestamps=None, **kw) -> dict:
     """One long audio as static shards (clip boundaries at multiples of ``shard_seconds``, no prompt carry-over: the sharded
     setting of SURVEY.md section 8e).  Inside a shard the walk is the reference's: a window starts at the shard's seek,
     and the seek then moves by the data-dependent amount of original_whisper.py:703-710, so the tail after the last closed
@@ -219,21 +234,45 @@ def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_wind
     condition_on_previous_text / initial_prompt: the tokens of a shard's kept segments are the prompt of its next window
     (``all_tokens[prompt_reset_since:]``, original_whisper.py:320-323,533,673-675,696-698), reset after a window decoded at
     temperature > 0.5; every shard starts from ``initial_prompt``.
+    clip_timestamps: only these [start, end) sections are transcribed (the reference's ``load_sections``,
+    audio/__init__.py:414-429: a window never crosses a section end, and a section is left once ``seek + 1 >= end``).  With
+    ``shard_seconds=None`` they are walked in order as ONE shard (shared prompt state, exactly the reference); otherwise every
+    clip is a shard of its own and the clips run batched side by side.
     -> dict(text, segments, language) in the shape of WhisperResult.to_dict (result.py:1398-1406)."""
     audio = audio.detach().float().flatten()
     total = int(audio.numel())
-    step = total if not shard_seconds else max(int(round(shard_seconds * SAMPLE_RATE)), 1)
-    shards = [[lo, min(lo + step, total)] for lo in range(0, max(total, 1), step)]          # [seek, end]
-    per_shard = [[] for _ in shards]
+    # a shard = a list of [start, end) sections walked in order + the index of the current one + the seek inside it
+    if clip_timestamps:
+        secs = [sc for sc in clip_sections(clip_timestamps, total)]
+        plans = [secs] if not shard_seconds else [[sc] for sc in secs]
+        slack = 1                                                        # `seek + 1 >= max_seek` ends a section
+    else:
+        step = total if not shard_seconds else max(int(round(shard_seconds * SAMPLE_RATE)), 1)
+        plans = [[[lo, min(lo + step, total)]] for lo in range(0, max(total, 1), step)]
+        slack = 0
+    cur = [0] * len(plans)                                               # current section of every shard
+    seek = [p[0][0] if p else 0 for p in plans]
+
+    def settle(i) -> bool:
+        """Move shard i to its next section while the current one is exhausted; False when the shard is finished."""
+        while cur[i] < len(plans[i]):
+            lo, hi = plans[i][cur[i]]
+            seek[i] = max(seek[i], lo)
+            if seek[i] + slack < hi:
+                return True
+            cur[i] += 1
+        return False
+
+    per_shard = [[] for _ in plans]
     init = tokenizer.encode(" " + initial_prompt.strip()) if initial_prompt is not None else []
-    all_tokens = [list(init) for _ in shards]
-    reset_since = [0] * len(shards)
+    all_tokens = [list(init) for _ in plans]
+    reset_since = [0] * len(plans)
     use_prompts = condition_on_previous_text or bool(init)
-    live = [i for i, (lo, hi) in enumerate(shards) if hi > lo]
+    live = [i for i in range(len(plans)) if plans[i] and settle(i)]
     while live:
         now, live = live[:batch_windows], live[batch_windows:]
-        part = [audio[shards[i][0]: min(shards[i][0] + N_SAMPLES, shards[i][1])] for i in now]
-        segs, info = transcribe_windows(model, tokenizer, part, time_offsets=[shards[i][0] / SAMPLE_RATE for i in now],
+        part = [audio[seek[i]: min(seek[i] + N_SAMPLES, plans[i][cur[i]][1])] for i in now]
+        segs, info = transcribe_windows(model, tokenizer, part, time_offsets=[seek[i] / SAMPLE_RATE for i in now],
                                         no_speech_threshold=no_speech_threshold, logprob_threshold=logprob_threshold,
                                         max_instant_words=max_instant_words, skip_silent=skip_silent,
                                         prompts=[all_tokens[i][reset_since[i]:] for i in now] if use_prompts else None, **kw)
@@ -244,8 +283,8 @@ def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_wind
                 all_tokens[i].extend(t for s in segs[k] for t in s["tokens"])
                 if not condition_on_previous_text or info["decode"][k].temperature > 0.5:
                     reset_since[i] = len(all_tokens[i])
-            shards[i][0] += max(int(info["advance"][k]), 1)
-            if shards[i][0] < shards[i][1]:
+            seek[i] += max(int(info["advance"][k]), 1)
+            if settle(i):
                 again.append(i)
         live = again + live
     segments = [s for ps in per_shard for s in ps]

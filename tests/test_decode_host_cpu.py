@@ -182,3 +182,28 @@ def test_transcribe_nonspeech_skip_and_avg_prob_threshold_match_unmodified_refer
     for sa, sb in zip(da["segments"], db["segments"]):
         assert sa["tokens"] == [int(t) for t in sb["tokens"]]
         assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
+
+
+@pytest.mark.parametrize("parallel", [False, True])
+def test_clip_timestamps_match_unmodified_reference(env, parallel):
+    """``clip_timestamps`` (the reference's load_sections): only the given sections are transcribed, a window never crosses a
+    section end.  Walked as ONE sequential shard (prompt carried across clips, exactly the reference) and as independent
+    shards batched side by side (equal to the reference with condition_on_previous_text=False)."""
+    import stable_whisper.whisper_word_level.original_whisper as ow
+    SP, om, stand = env["SP"], env["om"], env["stand"]
+    audio = torch.cat([SP.synth_audio(480000, seed=81), SP.synth_audio(480000, seed=82), SP.synth_audio(200000, seed=83)])
+    clips = [2.5, 21.0, 30.0, 65.5, 66.0]                      # two closed clips (one longer than a window) and an open one
+    carry = not parallel
+    theirs = ow.transcribe_stable(om, audio, language="en", temperature=0.0, condition_on_previous_text=carry, word_timestamps=True,
+                                  vad=False, suppress_silence=False, suppress_ts_tokens=False, regroup=False, verbose=None,
+                                  fp16=False, ignore_compatibility=True, sample_len=16, clip_timestamps=clips)
+    mine = stand.transcribe(audio, language="en", temperature=0.0, condition_on_previous_text=carry, regroup=False,
+                            sample_len=16, shard_seconds=30.0 if parallel else None, batch_windows=4, clip_timestamps=clips,
+                            suppress_silence=False)
+    da, db = mine.to_dict(), theirs.to_dict()
+    assert [s["seek"] for s in da["segments"]] == [s["seek"] for s in db["segments"]] and len(da["segments"]) >= 3
+    for sa, sb in zip(da["segments"], db["segments"]):
+        assert sa["tokens"] == [int(t) for t in sb["tokens"]]
+        assert sa["start"] == sb["start"] and sa["end"] == sb["end"]
+        for wa, wb in zip(sa["words"], sb["words"]):
+            assert wa["tokens"] == wb["tokens"] and wa["start"] == wb["start"] and wa["end"] == wb["end"]
