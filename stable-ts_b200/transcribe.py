@@ -145,6 +145,8 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                             jump[b] = round(float(ends[k]) * SAMPLE_RATE)
                         else:                                 # the window ends where the long silence begins
                             n_samples[b] = int(starts[k] * SAMPLE_RATE)
+                            if dev_audio is batch:            # the caller's own device tensor: do not write into it
+                                dev_audio = dev_audio.clone()
                             dev_audio[b, n_samples[b]:] = 0
         if suppress_ts_tokens and ts_token_mask is None and any(m is not None for m in masks):
             ts_token_mask = masks
