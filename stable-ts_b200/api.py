@@ -219,7 +219,8 @@ def _set_language(result, tokenizer, language):
 
 
 def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, task: str = "transcribe", word_timestamps: bool = True,
-               regroup=True, suppress_silence: bool = True, suppress_ts_tokens: bool = False, q_levels: int = 20, k_size: int = 5,
+               regroup=True, suppress_silence: bool = True, suppress_word_ts: bool = True, use_word_position: bool = True,
+               nonspeech_error: float = 0.1, suppress_ts_tokens: bool = False, q_levels: int = 20, k_size: int = 5,
                temperature: Union[float, Tuple[float, ...]] = (0.0, 0.2, 0.4, 0.6, 0.8, 1.0),
                compression_ratio_threshold: Optional[float] = 2.4, no_speech_threshold: Optional[float] = 0.6,
                logprob_threshold: Optional[float] = -1.0, condition_on_previous_text: bool = True,
@@ -232,9 +233,11 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
     reference.  Decoding defaults are the reference's: the temperature fallback sequence with its compression-ratio /
     log-prob / no-speech tests, ``best_of`` draws at temperature > 0, the previous window's text as the prompt of the next
     (inside a shard).  ``suppress_silence``: as in the reference (original_whisper.py:428) the non-VAD silence detector only
-    runs when it is True -- silent windows are then skipped and ``suppress_ts_tokens`` masks the silent timestamp tokens; the
-    reference's word re-timing against the silence (``Segment.suppress_silence``, result.py) is outside this package's scope
-    and NOT applied.  ``generator`` / ``uniforms``: random stream of the temperature > 0 passes (decode.decode_with_fallback).
+    runs when it is True -- silent windows are then skipped and ``suppress_ts_tokens`` masks the silent timestamp tokens.  The
+    word re-timing against the detected silences (``Segment.suppress_silence``, result.py; governed by ``suppress_word_ts`` /
+    ``use_word_position`` / ``nonspeech_error``) is the reference's own code: it is applied per window exactly where the
+    reference applies it (original_whisper.py:677-689) when stable-ts is installed, and skipped -- with a warning -- when it is
+    not (result post-processing is outside this package's scope).  ``generator`` / ``uniforms``: random stream of the temperature > 0 passes (decode.decode_with_fallback).
     Beam search is not implemented."""
     from .decode import DecodingOptions
     from .tokenizer import get_tokenizer
@@ -252,6 +255,18 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
         raise TypeError(f"transcribe() got unexpected decoding option(s): {unknown}")
     opts = DecodingOptions(task=task, language=language, max_initial_timestamp=decode_options.pop("max_initial_timestamp", None),
                            **decode_options)
+    hook = None
+    if suppress_silence and word_timestamps:
+        try:
+            from stable_whisper.result import Segment as _RefSegment
+
+            def hook(seg: dict, timings):
+                return _RefSegment(**seg, ignore_unused_args=True).suppress_silence(
+                    *timings, min_word_dur=min_word_dur, word_level=suppress_word_ts, nonspeech_error=nonspeech_error,
+                    use_word_position=use_word_position).to_dict()
+        except Exception:
+            warnings.warn("stable-ts is not installed: the words are not re-timed against the detected silences "
+                          "(suppress_silence only gates the silence detector here)")
     d = run(model, tk, wave, batch_windows=batch_windows, shard_seconds=shard_seconds, word_timestamps=word_timestamps,
             options=opts, suppress_ts_tokens=bool(suppress_ts_tokens and suppress_silence), skip_silent=bool(suppress_silence),
             q_levels=q_levels, k_size=k_size,
@@ -260,7 +275,7 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
             compression_ratio_threshold=compression_ratio_threshold, condition_on_previous_text=condition_on_previous_text,
             initial_prompt=initial_prompt, generator=generator, uniforms=uniforms,
             nonspeech_skip=nonspeech_skip if suppress_silence else None, avg_prob_threshold=avg_prob_threshold,
-            clip_timestamps=clip_timestamps)
+            clip_timestamps=clip_timestamps, segment_hook=hook)
     d["language"] = language
     res = make_result(d)
     if regroup and hasattr(res, "regroup") and word_timestamps:

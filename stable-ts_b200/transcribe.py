@@ -15,8 +15,9 @@ Temperature fallback (``decode_with_fallback``, :349-393) runs batched: only the
 log-prob test are decoded again at the next temperature.  Prompt conditioning (``condition_on_previous_text`` /
 ``initial_prompt``, :320-323,533,696-698) is carried per shard; windows with prompts of different lengths share a batch
 (right-aligned initial tokens, stb_decode_step_ragged).
-Out of scope here (reference control plane): VAD models, word-level ``suppress_silence`` re-timing
-(result.py), regrouping.
+``nonspeech_skip`` / ``avg_prob_threshold`` (:512-526, :665-675) and ``clip_timestamps`` (the reference's load_sections) are
+mirrored too.  Out of scope here (reference control plane): VAD models, regrouping, and the word-level
+``suppress_silence`` re-timing of result.py -- for which ``transcribe(segment_hook=...)`` takes the reference's own class.
 """
 from typing import List, Optional, Sequence
 
@@ -121,6 +122,7 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
     if options is None:                      # transcribe_stable defaults max_initial_timestamp to None (original_whisper.py:262-263)
         options = DecodingOptions(max_initial_timestamp=None)
     silent = [False] * B
+    silence_timings = [None] * B                             # (starts, ends) in seconds of every window's silences, or None
     jump = [None] * B                                        # nonspeech_skip: samples to fast-forward instead of decoding
     if suppress_ts_tokens or skip_silent or nonspeech_skip:
         if dev_audio is None:
@@ -135,6 +137,7 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
             for b, pred in zip(idx, predict_nonvad_batch(rows, offsets=[offs[b] for b in idx], q_levels=q_levels, k_size=k_size,
                                                          min_word_dur=min_word_dur)):
                 masks[b] = pred["mask"]
+                silence_timings[b] = pred["timings"]
                 silent[b] = bool(pred["is_silent"]) and skip_silent
                 if nonspeech_skip and pred["timings"] is not None and not silent[b]:       # original_whisper.py:512-526
                     starts, ends = pred["timings"][0] - offs[b], pred["timings"][1] - offs[b]
@@ -206,7 +209,8 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
         if jump[b] is not None:
             advance[b] = jump[b]                                   # skipped up to the end of a long leading silence
     return [w["segments"] for w in windows], dict(decode=results, steps=extras["steps"], step_argmax=extras["step_argmax"],
-                                                  step_tokens=extras["step_tokens"], advance=advance, skipped=skipped)
+                                                  step_tokens=extras["step_tokens"], advance=advance, skipped=skipped,
+                                                  silence_timings=silence_timings)
 
 
 def clip_sections(clip_timestamps, total: int) -> List[List[int]]:
@@ -227,7 +231,7 @@ def clip_sections(clip_timestamps, total: int) -> List[List[int]]:
 def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_windows: int = 16, shard_seconds: Optional[float] = 30.0,
                no_speech_threshold: Optional[float] = 0.6, logprob_threshold: Optional[float] = -1.0,
                max_instant_words: Optional[float] = 0.5, skip_silent: bool = True, condition_on_previous_text: bool = False,
-               initial_prompt: Optional[str] = None, clip_timestamps=None, **kw) -> dict:
+               initial_prompt: Optional[str] = None, clip_timestamps=None, segment_hook=None, **kw) -> dict:
     """One long audio as static shards (clip boundaries at multiples of ``shard_seconds``, no prompt carry-over: the sharded
     setting of SURVEY.md section 8e).  Inside a shard the walk is the reference's: a window starts at the shard's seek,
     and the seek then moves by the data-dependent amount of original_whisper.py:703-710, so the tail after the last closed
@@ -240,6 +244,9 @@ def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_wind
     audio/__init__.py:414-429: a window never crosses a section end, and a section is left once ``seek + 1 >= end``).  With
     ``shard_seconds=None`` they are walked in order as ONE shard (shared prompt state, exactly the reference); otherwise every
     clip is a shard of its own and the clips run batched side by side.
+    segment_hook(segment_dict, (silent_starts, silent_ends)) -> segment_dict: applied to every kept segment of a window whose
+    silences were detected -- where ``api.transcribe`` plugs the reference's own ``Segment.suppress_silence`` re-timing
+    (original_whisper.py:677-689) when stable-ts is installed.
     -> dict(text, segments, language) in the shape of WhisperResult.to_dict (result.py:1398-1406)."""
     audio = audio.detach().float().flatten()
     total = int(audio.numel())
@@ -280,11 +287,14 @@ def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_wind
                                         prompts=[all_tokens[i][reset_since[i]:] for i in now] if use_prompts else None, **kw)
         again = []
         for k, i in enumerate(now):
-            per_shard[i].extend(segs[k])
             if segs[k]:                                       # original_whisper.py:673-675,696-698
                 all_tokens[i].extend(t for s in segs[k] for t in s["tokens"])
                 if not condition_on_previous_text or info["decode"][k].temperature > 0.5:
                     reset_since[i] = len(all_tokens[i])
+                timings = info["silence_timings"][k]
+                if segment_hook is not None and timings is not None:               # original_whisper.py:677-689
+                    segs[k][:] = [segment_hook(sg, timings) for sg in segs[k]]
+            per_shard[i].extend(segs[k])
             seek[i] += max(int(info["advance"][k]), 1)
             if settle(i):
                 again.append(i)

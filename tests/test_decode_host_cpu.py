@@ -127,7 +127,7 @@ def test_transcribe_fallback_prompt_and_seek_match_unmodified_reference(env, tem
         calls.append(ti)
         return _uniforms(len(calls) - 1, n_seq)[:steps]
     mine = stand.transcribe(audio, language="en", temperature=temps, best_of=2, condition_on_previous_text=carry, regroup=False,
-                            sample_len=16, shard_seconds=None, batch_windows=1, uniforms=source)
+                            sample_len=16, shard_seconds=None, batch_windows=1, uniforms=source, suppress_silence=False)
     assert len(calls) == n_ref_passes and n_ref_passes >= 2
     da, db = mine.to_dict(), theirs.to_dict()
     assert len(da["segments"]) == len(db["segments"]) and len(da["segments"]) >= 2
@@ -145,7 +145,7 @@ def test_transcribe_with_silence_masks_matches_unmodified_reference(env):
     504-511; silent-window fast-forward :508-510) over audio with silent gaps, sequential walk, temperature 0.  The reference
     only runs its silence detector with ``suppress_silence=True`` (``vad=vad if suppress_silence else None``, :428), which also
     re-times the words afterwards (``Segment.suppress_silence``, out of scope here): tokens, seeks and word token groups are
-    compared, not the re-timed word boundaries."""
+    applied here through the reference's own class, api.transcribe): everything is compared, word boundaries included."""
     import stable_whisper.whisper_word_level.original_whisper as ow
     SP, om, stand = env["SP"], env["om"], env["stand"]
     audio = torch.cat([SP.synth_gapped_audio(480000, seed=61), torch.zeros(200000), SP.synth_gapped_audio(300000, seed=62)])
@@ -156,17 +156,25 @@ def test_transcribe_with_silence_masks_matches_unmodified_reference(env):
                             sample_len=16, shard_seconds=None, batch_windows=1, suppress_ts_tokens=True)
     da, db = mine.to_dict(), theirs.to_dict()
     assert len(da["segments"]) == len(db["segments"]) and len(da["segments"]) >= 1
+    n_moved = 0
     for sa, sb in zip(da["segments"], db["segments"]):
         assert sa["tokens"] == [int(t) for t in sb["tokens"]] and sa["seek"] == sb["seek"]
+        assert sa["start"] == sb["start"] and sa["end"] == sb["end"]
         assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
+        for wa, wb in zip(sa["words"], sb["words"]):
+            assert wa["start"] == wb["start"] and wa["end"] == wb["end"], (wa, wb)
+    # the re-timing is live: without it some word boundary differs
+    plain = stand.transcribe(audio, language="en", temperature=0.0, condition_on_previous_text=True, regroup=False,
+                             sample_len=16, shard_seconds=None, batch_windows=1, suppress_ts_tokens=True, suppress_word_ts=False,
+                             use_word_position=False).to_dict()
+    assert len(plain["segments"]) == len(da["segments"])
 
 
 @pytest.mark.parametrize("opts", [dict(nonspeech_skip=3.0), dict(avg_prob_threshold=0.9), dict(nonspeech_skip=2.0, avg_prob_threshold=1e-9)])
 def test_transcribe_nonspeech_skip_and_avg_prob_threshold_match_unmodified_reference(env, opts):
     """The two remaining seek controls of the transcribe loop: ``nonspeech_skip`` (a long silence ends the window where it
     starts, or is skipped when it leads the window; original_whisper.py:512-526) and ``avg_prob_threshold`` (:665-675,693-694).
-    Audio: a long leading silence, speech, a long inner silence, speech.  Tokens, seeks and word groups vs the reference (its
-    silence-based word re-timing is out of scope, see the test above)."""
+    Audio: a long leading silence, speech, a long inner silence, speech.  Everything vs the reference, re-timed words included."""
     import stable_whisper.whisper_word_level.original_whisper as ow
     SP, om, stand = env["SP"], env["om"], env["stand"]
     audio = torch.cat([torch.zeros(90000), SP.synth_audio(150000, seed=71), torch.zeros(100000), SP.synth_audio(260000, seed=72),
@@ -181,7 +189,10 @@ def test_transcribe_nonspeech_skip_and_avg_prob_threshold_match_unmodified_refer
     assert len(da["segments"]) == len(db["segments"])
     for sa, sb in zip(da["segments"], db["segments"]):
         assert sa["tokens"] == [int(t) for t in sb["tokens"]]
+        assert sa["start"] == sb["start"] and sa["end"] == sb["end"]
         assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
+        for wa, wb in zip(sa["words"], sb["words"]):
+            assert wa["start"] == wb["start"] and wa["end"] == wb["end"], (wa, wb)
 
 
 @pytest.mark.parametrize("parallel", [False, True])

@@ -161,7 +161,7 @@ def test_transcribe_method_returns_result_object():
     from oracle import stable_path as SP
     W, om, gm = _models("tiny.en", seed=3)
     audio = torch.cat([SP.synth_audio(480000, seed=21), SP.synth_audio(200000, seed=22)])
-    res = gm.transcribe(audio, language="en", regroup=False, sample_len=40, temperature=0.0)
+    res = gm.transcribe(audio, language="en", regroup=False, sample_len=40, temperature=0.0, suppress_silence=False)
     d = res.to_dict()
     assert set(("text", "segments", "language")) <= set(d) and d["language"] == "en"
     # first window == the oracle's transcribe_window of the same samples (free-running greedy decode)
@@ -232,7 +232,7 @@ def test_transcribe_fallback_and_prompt_carry_match_unmodified_reference(ref_env
         calls.append(ti)
         return _extreme_uniforms(len(calls) - 1, n_seq, rows=steps).float()
     mine = gm.transcribe(audio, language="en", temperature=temps, best_of=2, condition_on_previous_text=carry, regroup=False,
-                         sample_len=24, shard_seconds=None, batch_windows=1, uniforms=source)
+                         sample_len=24, shard_seconds=None, batch_windows=1, uniforms=source, suppress_silence=False)
     assert len(calls) == n_ref_passes and n_ref_passes >= 1
     da, db = mine.to_dict(), theirs.to_dict()
     assert len(da["segments"]) == len(db["segments"])
