@@ -227,6 +227,8 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
                initial_prompt: Optional[str] = None, max_instant_words: Optional[float] = 0.5, gap_padding: str = " ...",
                min_word_dur: float = 0.1, batch_windows: int = 16, shard_seconds: Optional[float] = 30.0, tokenizer=None,
                nonspeech_skip: Optional[float] = None, avg_prob_threshold: Optional[float] = None, clip_timestamps=None,
+               dynamic_heads=None, aligner="legacy", extra_models=None, prepend_punctuations: Optional[str] = None,
+               append_punctuations: Optional[str] = None, split_callback=None,
                generator: Optional[torch.Generator] = None, uniforms=None, **decode_options):
     """``model.transcribe`` (transcribe_stable, original_whisper.py:27-78): -> WhisperResult.  Static 30 s shards batched
     ``batch_windows`` at a time (transcribe.py); ``shard_seconds=None`` walks the audio as one sequential shard like the
@@ -275,7 +277,9 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
             compression_ratio_threshold=compression_ratio_threshold, condition_on_previous_text=condition_on_previous_text,
             initial_prompt=initial_prompt, generator=generator, uniforms=uniforms,
             nonspeech_skip=nonspeech_skip if suppress_silence else None, avg_prob_threshold=avg_prob_threshold,
-            clip_timestamps=clip_timestamps, segment_hook=hook)
+            clip_timestamps=clip_timestamps, segment_hook=hook, dynamic_heads=dynamic_heads, aligner=aligner,
+            extra_models=extra_models, prepend_punctuations=prepend_punctuations, append_punctuations=append_punctuations,
+            split_callback=split_callback)
     d["language"] = language
     res = make_result(d)
     if regroup and hasattr(res, "regroup") and word_timestamps:

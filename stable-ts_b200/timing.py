@@ -391,15 +391,23 @@ PREPEND_PUNCT = "\"'“¿([{-"
 APPEND_PUNCT = "\"'.。,，!！?？:：”)]}、"
 
 
-def _prepare_word_timestamps(segments, tokenizer, split_callback, gap_padding, pad_first_seg):
+def _prepare_word_timestamps(segments, tokenizer, split_callback, gap_padding, pad_first_seg, char_split: bool = False):
+    """-> (text_tokens, words, word_tokens, seg_indices, ignore_tokens, word_tokens_out); the last two are None unless
+    ``char_split`` (the "new" aligner's character-level script: no gap padding, timing.py:380-390,442-444)."""
     for seg in segments:
         seg["words"] = []
-    text_tokens, (words, word_tokens), seg_indices = split_word_tokens(segments, tokenizer, padding=gap_padding,
+    text_tokens, (words, word_tokens), seg_indices = split_word_tokens(segments, tokenizer,
+                                                                       padding=None if char_split else gap_padding,
                                                                        split_callback=split_callback,
-                                                                       pad_first_seg=pad_first_seg)
+                                                                       pad_first_seg=pad_first_seg, char_split=char_split)
     words = list(words) + [tokenizer.decode([tokenizer.eot])]
+    itk = orig = None
+    if isinstance(word_tokens, dict):
+        orig = list(word_tokens["tokens_orig"]) + [[tokenizer.eot]]
+        itk = word_tokens["ignore_tokens"]
+        word_tokens = word_tokens["tokens"]
     word_tokens = list(word_tokens) + [[tokenizer.eot]]
-    return text_tokens, words, word_tokens, seg_indices
+    return text_tokens, words, word_tokens, seg_indices, itk, orig
 
 
 def _finish_word_timestamps(segments, alignment, seg_indices, prepend_punctuations, append_punctuations, min_word_dur,
@@ -427,34 +435,38 @@ def add_word_timestamps_batch(windows: List[dict], model: B200Whisper, tokenizer
                               prepend_punctuations: Optional[str] = PREPEND_PUNCT,
                               append_punctuations: Optional[str] = APPEND_PUNCT, min_word_dur: float = 0.1,
                               split_callback: Optional[Callable] = None, gap_padding: Optional[str] = " ...",
-                              pad_first_seg: bool = True, medfilt_width: int = 7, qk_scale: float = 1.0):
+                              pad_first_seg: bool = True, medfilt_width: int = 7, qk_scale: float = 1.0, dynamic_heads=None,
+                              aligner: Union[str, dict] = "legacy", extra_models=None):
     """Batched ``add_word_timestamps_stable``: ``windows`` = list of dict(segments, num_samples[, audio]); all windows
     share ONE encoder/decoder/DTW batch (``enc`` = the dict from ``model.encode`` for the same windows, in order).
-    Windows without segments are skipped (timing.py:430-431)."""
+    Windows without segments are skipped (timing.py:430-431).  ``dynamic_heads`` / ``aligner`` / ``extra_models`` as in
+    ``add_word_timestamps_stable``; ``extra_models`` need ``audio`` in every window dict.  ``char_split`` is popped from the
+    caller's ``aligner`` dict exactly as the reference pops it (timing.py:442), so -- as there -- only the FIRST window
+    processed with that dict is character-split."""
     min_word_dur = min_word_dur or 0
     prepend_punctuations = PREPEND_PUNCT if prepend_punctuations is None else prepend_punctuations
     append_punctuations = APPEND_PUNCT if append_punctuations is None else append_punctuations
     live = [i for i, w in enumerate(windows) if len(w["segments"]) > 0]
     if not live:
         return
-    prep = {i: _prepare_word_timestamps(windows[i]["segments"], tokenizer, split_callback, gap_padding, pad_first_seg)
-            for i in live}
+    char_split = bool(isinstance(aligner, dict) and aligner.pop("char_split", False))
+    pads = {i: (None if (char_split and i == live[0]) else gap_padding) for i in live}
+    prep = {i: _prepare_word_timestamps(windows[i]["segments"], tokenizer, split_callback, pads[i], pad_first_seg,
+                                        char_split=char_split and i == live[0]) for i in live}
     jobs = [WindowJob(list(prep[i][0]), int(windows[i]["num_samples"]), windows[i].get("audio")) for i in live]
     sub = enc
     if enc is None or len(live) != enc["B"]:
         ckv = None                                          # cached cross K/V only matches the full batch
     if enc is not None and len(live) != enc["B"]:
-        idx = torch.tensor(live, device=model.device)
-        T = L.N_AUDIO_CTX
-        rows = (idx[:, None] * T + torch.arange(T, device=model.device)[None]).reshape(-1)
-        sub = {"f32": enc["f32"].index_select(0, idx), "hi": enc["hi"].index_select(0, rows),
-               "lo": None if enc["lo"] is None else enc["lo"].index_select(0, rows), "B": len(live)}
-    res = align_windows(model, tokenizer, jobs, medfilt_width=medfilt_width, qk_scale=qk_scale, enc=sub, ckv=ckv)
+        from .decode import enc_select
+        sub = enc_select(enc, live)
+    res = align_windows(model, tokenizer, jobs, medfilt_width=medfilt_width, qk_scale=qk_scale, enc=sub, ckv=ckv,
+                        dynamic_heads=dynamic_heads, aligner=aligner, extra_models=extra_models)
     for (jumps, probs), i in zip(res, live):
-        _, words, word_tokens, seg_indices = prep[i]
-        alignment = word_timings_from_jumps(jumps, probs, words, word_tokens)
+        _, words, word_tokens, seg_indices, itk, orig = prep[i]
+        alignment = word_timings_from_jumps(jumps, probs, words, word_tokens, ignore_tokens=itk, word_tokens_out=orig)
         _finish_word_timestamps(windows[i]["segments"], alignment, seg_indices, prepend_punctuations, append_punctuations,
-                                min_word_dur, gap_padding, pad_first_seg)
+                                min_word_dur, pads[i], pad_first_seg)
 
 
 def add_word_timestamps_stable(*, segments: List[dict], model: B200Whisper, tokenizer, audio: Optional[torch.Tensor] = None,

@@ -82,7 +82,9 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
                        max_instant_words: Optional[float] = None, temperature=0.0,
                        compression_ratio_threshold: Optional[float] = None, prompts=None,
                        generator: Optional[torch.Generator] = None, uniforms=None, nonspeech_skip: Optional[float] = None,
-                       avg_prob_threshold: Optional[float] = None):
+                       avg_prob_threshold: Optional[float] = None, dynamic_heads=None, aligner="legacy", extra_models=None,
+                       prepend_punctuations: Optional[str] = None, append_punctuations: Optional[str] = None,
+                       split_callback=None):
     """B independent <=30 s windows -> (list (per window) of segment dicts with ``words``, info).
     ``enc`` (+ ``n_samples``) may be passed instead of ``audios`` when the encoder output is already on the device.
 
@@ -97,6 +99,8 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
     ``min_word_dur`` of the window start, the window is skipped up to the silence's end (original_whisper.py:512-526).
     avg_prob_threshold: a window that ends on a single timestamp and whose words average below it is dropped; otherwise the
     seek moves to the end of the last word (original_whisper.py:665-675,693-694).
+    dynamic_heads / aligner / extra_models / prepend_punctuations / append_punctuations / split_callback: the word-timestamp
+    options of ``add_word_timestamps_stable`` (original_whisper.py:635-651), passed to the batched alignment pass.
     info["advance"][b]: samples the reference's seek would move by after this window (original_whisper.py:703-710)."""
     dev_audio = None
     if enc is None:
@@ -184,13 +188,18 @@ def transcribe_windows(model: B200Whisper, tokenizer, audios: Sequence[torch.Ten
         for s in segs:
             s["seek"] = offs[b]
         num = min(round(end_pos * N_SAMPLES_PER_TOKEN), n_samples[b]) if end_pos > 0 else n_samples[b]
-        windows.append(dict(segments=segs, num_samples=num))
+        win = dict(segments=segs, num_samples=num)
+        if extra_models and dev_audio is not None:           # every extra model runs its own front end on the window
+            win["audio"] = dev_audio[b, : n_samples[b]].cpu()
+        windows.append(win)
         advance.append(n_samples[b] if (skip or single_ending or not len(toks)) else num)
         skipped.append(bool(skip))
         single.append(bool(single_ending))
     if word_timestamps:
         add_word_timestamps_batch(windows, model, tokenizer, enc=enc, ckv=extras["ckv"] if ckv_valid else None,
-                                  gap_padding=gap_padding, min_word_dur=min_word_dur)
+                                  gap_padding=gap_padding, min_word_dur=min_word_dur, dynamic_heads=dynamic_heads,
+                                  aligner=aligner, extra_models=extra_models, prepend_punctuations=prepend_punctuations,
+                                  append_punctuations=append_punctuations, split_callback=split_callback)
         if max_instant_words is not None:                          # original_whisper.py:655-663
             for w in windows:
                 w["segments"] = [s for s in w["segments"] if not s["words"] or float(np.mean(np.array(

@@ -218,3 +218,40 @@ def test_clip_timestamps_match_unmodified_reference(env, parallel):
         assert sa["start"] == sb["start"] and sa["end"] == sb["end"]
         for wa, wb in zip(sa["words"], sb["words"]):
             assert wa["tokens"] == wb["tokens"] and wa["start"] == wb["start"] and wa["end"] == wb["end"]
+
+
+@pytest.mark.parametrize("variant", ["new", "dynamic", "extra_models", "char_split", "punctuation"])
+def test_transcribe_word_timestamp_variants_match_unmodified_reference(env, variant):
+    """The word-timestamp options of ``add_word_timestamps_stable`` through the whole transcribe walk (original_whisper.py:
+    635-651): the "new" aligner, dynamic heads, ``extra_models``, ``char_split`` (popped from the shared dict by the first
+    window, as in the reference) and custom punctuation sets."""
+    import oracle.whisper_ref as W
+    import stable_whisper.whisper_word_level.original_whisper as ow
+    from standin import OracleBackedModel
+    SP, om, stand = env["SP"], env["om"], env["stand"]
+    audio = torch.cat([SP.synth_audio(480000, seed=91), SP.synth_audio(250000, seed=92)])
+    ref_kw, kw = {}, {}
+    if variant == "new":
+        ref_kw, kw = dict(aligner="new"), dict(aligner="new")
+    elif variant == "dynamic":
+        ref_kw, kw = dict(dynamic_heads="3,2"), dict(dynamic_heads="3,2")
+    elif variant == "extra_models":
+        om2 = W.build_model("tiny.en", seed=4)
+        ref_kw, kw = dict(extra_models=[om2]), dict(extra_models=[OracleBackedModel(om2)])
+    elif variant == "char_split":
+        ref_kw, kw = dict(aligner={"char_split": True}), dict(aligner={"char_split": True})
+    else:
+        ref_kw = kw = dict(prepend_punctuations="(", append_punctuations=".,")
+    theirs = ow.transcribe_stable(om, audio, language="en", temperature=0.0, condition_on_previous_text=False, word_timestamps=True,
+                                  vad=False, suppress_silence=False, suppress_ts_tokens=False, regroup=False, verbose=None,
+                                  fp16=False, ignore_compatibility=True, sample_len=16, **ref_kw)
+    mine = stand.transcribe(audio, language="en", temperature=0.0, condition_on_previous_text=False, regroup=False,
+                            sample_len=16, shard_seconds=None, batch_windows=1, suppress_silence=False, **kw)
+    da, db = mine.to_dict(), theirs.to_dict()
+    assert [s["seek"] for s in da["segments"]] == [s["seek"] for s in db["segments"]] and len(da["segments"]) >= 2
+    for sa, sb in zip(da["segments"], db["segments"]):
+        assert sa["tokens"] == [int(t) for t in sb["tokens"]] and sa["start"] == sb["start"] and sa["end"] == sb["end"]
+        assert [w["tokens"] for w in sa["words"]] == [w["tokens"] for w in sb["words"]]
+        for wa, wb in zip(sa["words"], sb["words"]):
+            assert wa["word"] == wb["word"] and wa["start"] == wb["start"] and wa["end"] == wb["end"], (wa, wb)
+            assert abs(wa["probability"] - wb["probability"]) <= 1e-5 * abs(wb["probability"])
