@@ -65,16 +65,25 @@ def test_ragged_prompts_and_caps_match_oracle_window_by_window(env):
         mel = W.pad_or_trim(W.log_mel_spectrogram(a, om.dims.n_mels), 3000)
         ref, _, _ = SP.decode_window(om, mel, language="en", sample_len=10, prompt=p or None, prefix=prefix)
         assert res[b].tokens == ref.tokens and abs(res[b].avg_logprob - ref.avg_logprob) < 1e-4
-    # n_ctx stop (decode.py:60): 1 + 223 + 1 = 225 initial tokens (tiny.en: sot_sequence is one token) leave room for 224 samples
-    # although sample_len is 230; the neighbour without a prompt runs the full script
-    forced = torch.randint(300, 40000, (230, 2), generator=g, dtype=torch.int32)
-    enc2 = stand.encode(stand.log_mel(torch.stack(audios[:2])))
-    res, ex = decode_windows(stand, tk, enc2, DecodingOptions(language="en", sample_len=230), prompts=[prompts[2], []],
+    # n_ctx stop (decode.py:60) on a model with a SHORT text context (n_text_ctx = 48: the stand-in engine recomputes the whole
+    # history every step): prompt cut to 48 // 2 - 1 = 23 tokens -> 1 + 23 + 1 = 25 initial tokens leave room for 24 samples
+    # although sample_len is 30; the neighbour without a prompt runs the full script
+    from oracle.whisper_ref.model import ModelDimensions
+    from standin import OracleBackedModel, OracleStepEngine
+    from stable_ts_b200.tokenizer import get_tokenizer
+    om_s = W.build_model(ModelDimensions(n_mels=80, n_audio_ctx=1500, n_audio_state=128, n_audio_head=2, n_audio_layer=1,
+                                         n_vocab=51864, n_text_ctx=48, n_text_state=128, n_text_head=2, n_text_layer=2), seed=8)
+    st_s = OracleBackedModel(om_s)
+    st_s.step_engine_cls = OracleStepEngine
+    tk_s = get_tokenizer(st_s, language="en", task="transcribe", synthetic=True)
+    forced = torch.randint(300, 40000, (30, 2), generator=g, dtype=torch.int32)
+    enc2 = st_s.encode(st_s.log_mel(torch.stack(audios[:2])))
+    res, ex = decode_windows(st_s, tk_s, enc2, DecodingOptions(language="en", sample_len=30), prompts=[prompts[2], []],
                              forced_tokens=forced)
-    assert ex["steps"] == 230 and len(res[0].tokens) == 224 and len(res[1].tokens) == 230
-    mel = W.pad_or_trim(W.log_mel_spectrogram(audios[0], om.dims.n_mels), 3000)
-    ref, _, rex = SP.decode_window(om, mel, language="en", sample_len=230, prompt=prompts[2], forced_tokens=forced[:, 0].tolist())
-    assert len(rex["step_argmax"]) == 224 and ex["step_argmax"][:224, 0].tolist() == rex["step_argmax"]
+    assert ex["steps"] == 30 and len(res[0].tokens) == 24 and len(res[1].tokens) == 30
+    mel = W.pad_or_trim(W.log_mel_spectrogram(audios[0], om_s.dims.n_mels), 3000)
+    ref, _, rex = SP.decode_window(om_s, mel, language="en", sample_len=30, prompt=prompts[2], forced_tokens=forced[:, 0].tolist())
+    assert len(rex["step_argmax"]) == 24 and ex["step_argmax"][:24, 0].tolist() == rex["step_argmax"]
     assert res[0].tokens == ref.tokens and abs(res[0].avg_logprob - ref.avg_logprob) < 1e-4
 
 
