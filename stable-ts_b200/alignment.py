@@ -7,11 +7,10 @@ refinement.py:44-47), so a reference install can drive them unchanged (INTEGRATI
 """
 from typing import List, Optional, Sequence
 
-import numpy as np
 import torch
 
 from .model import B200Whisper
-from .timing import WindowJob, add_word_timestamps_stable, align_windows, n_frames_for, token_row, word_timings_from_jumps
+from .timing import WindowJob, add_word_timestamps_stable, align_windows, token_row, word_timings_from_jumps
 
 N_SAMPLES = 480000
 

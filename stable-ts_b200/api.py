@@ -16,7 +16,7 @@ the built-in drivers (transcribe.py, locate.py).
 import os
 import warnings
 from types import MethodType
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import Optional, Tuple, Union
 
 import torch
 

@@ -10,7 +10,7 @@ greedily decodes it token by token, forcing the target tokens when they are prob
 ``stb_qk_postprocess`` with S = 0 and all rows / ``stb_dtw``); (b) is a data-dependent, one-token-at-a-time host loop in the
 reference as well, and runs here over the KV-cached ``stb_decode_step`` through the whisper-protocol decoder of shim.py.
 """
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import List, Sequence, Tuple, Union
 
 import numpy as np
 import torch

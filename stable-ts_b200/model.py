@@ -11,7 +11,6 @@ Weight layout handed to the kernels (all caller-owned torch tensors kept alive i
   * LayerNorm / bias / positional tables in fp32; token embedding both fp32 (gather) and split (logits GEMM).
 """
 import ctypes
-import math
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 

@@ -9,8 +9,8 @@ vice versa.  The same dict is the wire format of the multi-GPU gather (sharding.
 Nothing here touches the GPU: these are host objects, as in the reference.
 """
 import json
-from dataclasses import dataclass, field
-from typing import Any, Dict, Iterable, List, Optional, Union
+from dataclasses import dataclass
+from typing import Any, List, Optional, Union
 
 SEGMENT_KEYS = ("start", "end", "text", "seek", "tokens", "temperature", "avg_logprob", "compression_ratio", "no_speech_prob")
 

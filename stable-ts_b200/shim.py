@@ -18,7 +18,7 @@ exactly that surface, so the UNMODIFIED reference functions run over the sm_100a
 
 These are host-side adapters: ``nn.Module`` is used only because the reference registers hooks through its API.
 """
-from typing import Dict, List, Optional
+from typing import List, Optional
 
 import torch
 from torch import nn

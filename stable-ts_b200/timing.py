@@ -15,12 +15,11 @@ import math
 import string
 from dataclasses import dataclass
 from itertools import chain
-from typing import Callable, List, Optional, Sequence, Tuple, Union
+from typing import Callable, List, Optional, Sequence, Union
 
 import numpy as np
 import torch
 
-from . import _lib as L
 from .model import B200Whisper
 
 N_SAMPLES = 480000
