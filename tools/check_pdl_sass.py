@@ -13,10 +13,15 @@ HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ALLOW = {            # kernel-name substring -> what its early non-coherent loads are (audited: constants only)
     "gemv_mma_kernel": "explicit __ldg of the WEIGHT fragments, issued ahead of the wait on purpose (gemv.cu:74)",
 }
+# Asynchronous copies (TMA `UTMALDG`, bulk `UBLKCP`) that are issued ahead of the wait ON PURPOSE -- listed with `--all`:
+#   decode_linear_kernel            the WEIGHT tiles of the first ring stages (the activations are loaded after the wait)
+#   decode_cross_attn(_tc)_kernel   the window's cross K / V tiles: written once per window batch by stb_cross_kv, many
+#                                   kernels earlier on the same stream (every kernel in between waited on its predecessor)
 
 
 def main():
-    targets = sys.argv[1:] or [os.path.join(HERE, "stable-ts_b200", "libstablets_b200.so")]
+    show_all = "--all" in sys.argv
+    targets = [a for a in sys.argv[1:] if a != "--all"] or [os.path.join(HERE, "stable-ts_b200", "libstablets_b200.so")]
     bad = 0
     for t in targets:
         out = subprocess.run(["cuobjdump", "-sass", t], capture_output=True, text=True).stdout
@@ -39,6 +44,8 @@ def main():
                 seen_wait = True
             elif not seen_wait and re.search(r"LDG\.E[.\w]*CONSTANT", line):
                 early.append(line.strip()[:100])
+            elif not seen_wait and show_all and re.search(r"UTMALDG|UBLKCP|\bLDG\.|\bLD\.E", line):
+                print("async/other early load in " + (fn or "?")[:70] + ": " + line.strip()[:70])
         flush()
     print(f"{bad} kernel(s) with non-coherent loads ahead of griddepcontrol.wait")
     return 1 if bad else 0
