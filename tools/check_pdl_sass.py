@@ -25,9 +25,12 @@ def main():
     bad = 0
     for t in targets:
         out = subprocess.run(["cuobjdump", "-sass", t], capture_output=True, text=True).stdout
-        fn, early, seen_wait = None, [], False
+        fn, early, other, seen_wait = None, [], [], False
         def flush():
             nonlocal bad
+            if fn and seen_wait and other:                 # --all: kernels WITH a wait only
+                for o in other:
+                    print("early (intentional, see above) in " + fn[:60] + ": " + o)
             if fn and seen_wait and early:
                 ok = any(k in fn for k in ALLOW)
                 print(("allowed " if ok else "EARLY   ") + fn)
@@ -38,14 +41,14 @@ def main():
             m = re.search(r"Function : (\S+)", line)
             if m:
                 flush()
-                fn, early, seen_wait = m.group(1), [], False
+                fn, early, other, seen_wait = m.group(1), [], [], False
                 continue
             if "ACQBULK" in line:
                 seen_wait = True
             elif not seen_wait and re.search(r"LDG\.E[.\w]*CONSTANT", line):
                 early.append(line.strip()[:100])
             elif not seen_wait and show_all and re.search(r"UTMALDG|UBLKCP|\bLDG\.|\bLD\.E", line):
-                print("async/other early load in " + (fn or "?")[:70] + ": " + line.strip()[:70])
+                other.append(line.strip()[:70])
         flush()
     print(f"{bad} kernel(s) with non-coherent loads ahead of griddepcontrol.wait")
     return 1 if bad else 0
