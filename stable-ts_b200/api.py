@@ -228,7 +228,8 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
                min_word_dur: float = 0.1, batch_windows: int = 16, shard_seconds: Optional[float] = 30.0, tokenizer=None,
                nonspeech_skip: Optional[float] = None, avg_prob_threshold: Optional[float] = None, clip_timestamps=None,
                dynamic_heads=None, aligner="legacy", extra_models=None, prepend_punctuations: Optional[str] = None,
-               append_punctuations: Optional[str] = None, split_callback=None,
+               append_punctuations: Optional[str] = None, split_callback=None, progress_callback=None,
+               verbose: Optional[bool] = False, ignore_compatibility: bool = False,
                generator: Optional[torch.Generator] = None, uniforms=None, **decode_options):
     """``model.transcribe`` (transcribe_stable, original_whisper.py:27-78): -> WhisperResult.  Static 30 s shards batched
     ``batch_windows`` at a time (transcribe.py); ``shard_seconds=None`` walks the audio as one sequential shard like the
@@ -240,7 +241,8 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
     ``use_word_position`` / ``nonspeech_error``) is the reference's own code: it is applied per window exactly where the
     reference applies it (original_whisper.py:677-689) when stable-ts is installed, and skipped -- with a warning -- when it is
     not (result post-processing is outside this package's scope).  ``generator`` / ``uniforms``: random stream of the temperature > 0 passes (decode.decode_with_fallback).
-    Beam search is not implemented."""
+    Beam search is not implemented.  ``progress_callback(seconds_done, total_seconds)`` as in the reference; ``verbose=True``
+    prints the segments; ``ignore_compatibility`` is accepted for call compatibility (there is no whisper version to check)."""
     from .decode import DecodingOptions
     from .tokenizer import get_tokenizer
     from .transcribe import transcribe as run
@@ -279,8 +281,11 @@ def transcribe(model: B200Whisper, audio, *, language: Optional[str] = None, tas
             nonspeech_skip=nonspeech_skip if suppress_silence else None, avg_prob_threshold=avg_prob_threshold,
             clip_timestamps=clip_timestamps, segment_hook=hook, dynamic_heads=dynamic_heads, aligner=aligner,
             extra_models=extra_models, prepend_punctuations=prepend_punctuations, append_punctuations=append_punctuations,
-            split_callback=split_callback)
+            split_callback=split_callback, progress_callback=progress_callback)
     d["language"] = language
+    if verbose:                                        # the reference prints every segment as it is produced; here at the end
+        for sg in d["segments"]:
+            print(f"[{sg['start']:.3f} --> {sg['end']:.3f}] {sg['text']}")
     res = make_result(d)
     if regroup and hasattr(res, "regroup") and word_timestamps:
         res.regroup(regroup)

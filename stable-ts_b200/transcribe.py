@@ -240,7 +240,8 @@ def clip_sections(clip_timestamps, total: int) -> List[List[int]]:
 def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_windows: int = 16, shard_seconds: Optional[float] = 30.0,
                no_speech_threshold: Optional[float] = 0.6, logprob_threshold: Optional[float] = -1.0,
                max_instant_words: Optional[float] = 0.5, skip_silent: bool = True, condition_on_previous_text: bool = False,
-               initial_prompt: Optional[str] = None, clip_timestamps=None, segment_hook=None, **kw) -> dict:
+               initial_prompt: Optional[str] = None, clip_timestamps=None, segment_hook=None, progress_callback=None,
+               **kw) -> dict:
     """One long audio as static shards (clip boundaries at multiples of ``shard_seconds``, no prompt carry-over: the sharded
     setting of SURVEY.md section 8e).  Inside a shard the walk is the reference's: a window starts at the shard's seek,
     and the seek then moves by the data-dependent amount of original_whisper.py:703-710, so the tail after the last closed
@@ -256,6 +257,8 @@ def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_wind
     segment_hook(segment_dict, (silent_starts, silent_ends)) -> segment_dict: applied to every kept segment of a window whose
     silences were detected -- where ``api.transcribe`` plugs the reference's own ``Segment.suppress_silence`` re-timing
     (original_whisper.py:677-689) when stable-ts is installed.
+    progress_callback(seconds_done, total_seconds): called after every round of windows (the reference's callback,
+    original_whisper.py:480-481; with several shards in flight ``seconds_done`` is the audio covered over all shards).
     -> dict(text, segments, language) in the shape of WhisperResult.to_dict (result.py:1398-1406)."""
     audio = audio.detach().float().flatten()
     total = int(audio.numel())
@@ -282,6 +285,8 @@ def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_wind
         return False
 
     per_shard = [[] for _ in plans]
+    covered = [0] * len(plans)                                           # samples walked per shard (progress reporting)
+    span = max(sum(hi - lo for p in plans for lo, hi in p), 1)
     init = tokenizer.encode(" " + initial_prompt.strip()) if initial_prompt is not None else []
     all_tokens = [list(init) for _ in plans]
     reset_since = [0] * len(plans)
@@ -304,10 +309,13 @@ def transcribe(model: B200Whisper, tokenizer, audio: torch.Tensor, *, batch_wind
                 if segment_hook is not None and timings is not None:               # original_whisper.py:677-689
                     segs[k][:] = [segment_hook(sg, timings) for sg in segs[k]]
             per_shard[i].extend(segs[k])
+            covered[i] += max(int(info["advance"][k]), 1)
             seek[i] += max(int(info["advance"][k]), 1)
             if settle(i):
                 again.append(i)
         live = again + live
+        if progress_callback is not None:
+            progress_callback(round(min(sum(covered), span) / SAMPLE_RATE, 2), round(span / SAMPLE_RATE, 2))
     segments = [s for ps in per_shard for s in ps]
     for k, s in enumerate(segments):
         s["id"] = k

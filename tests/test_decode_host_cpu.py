@@ -264,3 +264,18 @@ def test_transcribe_word_timestamp_variants_match_unmodified_reference(env, vari
         for wa, wb in zip(sa["words"], sb["words"]):
             assert wa["word"] == wb["word"] and wa["start"] == wb["start"] and wa["end"] == wb["end"], (wa, wb)
             assert abs(wa["probability"] - wb["probability"]) <= 1e-5 * abs(wb["probability"])
+
+
+def test_progress_callback_and_unknown_options(env):
+    SP, stand = env["SP"], env["stand"]
+    audio = torch.cat([SP.synth_audio(480000, seed=95), SP.synth_audio(100000, seed=96)])
+    seen = []
+    res = stand.transcribe(audio, language="en", temperature=0.0, regroup=False, sample_len=8, shard_seconds=None,
+                           suppress_silence=False, progress_callback=lambda done, total: seen.append((done, total)),
+                           verbose=None, ignore_compatibility=True)
+    assert seen and seen[-1][0] == seen[-1][1] == round(580000 / 16000, 2) and all(a[0] <= b[0] for a, b in zip(seen, seen[1:]))
+    assert len(res.to_dict()["segments"]) >= 1
+    with pytest.raises(TypeError):
+        stand.transcribe(audio, language="en", vad=True)
+    with pytest.raises(NotImplementedError):
+        stand.transcribe(audio, language="en", beam_size=5)
