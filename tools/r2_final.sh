@@ -1,4 +1,6 @@
 #!/bin/bash
+# SUPERSEDED by tools/r2_final3.sh: this first attempt kept three `ncu --set full` reports (71 MB) under gpurun_out/ and
+# gpurun returns at most 64 MiB, so nothing came back but the stdout tail (profiles/r2_final_call1_stdout.txt).
 # Round-2 final GPU call: the whole -m gpu suite, the headline bench + the reference arm, the other BASELINE configurations
 # (base single clip, small align x64, large-v3 refine), the ncu launch list of a (shortened) step and full captures of the
 # heaviest kernels.
